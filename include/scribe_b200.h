@@ -1,0 +1,143 @@
+/*
+ * scribe_b200.h -- C-ABI of the B200-native replacement for Scribe-py's pairwise-causality hot path.
+ *
+ * The reference (aristoteleo/Scribe-py) is pure Python and has no FFI; its seams for this path are plain
+ * Python callables.  Each entry point below names the reference callable(s) it stands in for
+ * (paths relative to the reference tree).  Python binds these with ctypes (scribe_py_b200/_lib.py);
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; scribe_last_error() gives the message
+ *     (thread-local).  Python maps codes onto the reference's exception types (see SCRIBE_E_*).
+ *   - "host" pointers are ordinary CPU memory owned by the caller; "dev" pointers are CUDA device memory
+ *     on the handle's device, owned by the caller.  The library keeps no caller pointer after return.
+ *   - point sets are passed dimension-major ("SoA"): x is dx rows of n contiguous doubles.
+ *   - calls on one handle are not re-entrant; use one handle per GPU / per thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with SCRIBE_E_CUDA.
+ */
+#ifndef SCRIBE_B200_H
+#define SCRIBE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCRIBE_ABI_VERSION 1
+#define SCRIBE_MAX_DIM   16   /* joint dimension dx+dy+dz accepted by the estimators          */
+#define SCRIBE_MAX_COND   4   /* conditioning genes per cRDI job (reference: L, causal_network.py:190) */
+#define SCRIBE_MAX_K     63   /* k and k_density upper bound                                    */
+
+/* status codes */
+#define SCRIBE_OK          0
+#define SCRIBE_E_ARG       1  /* bad argument (-> ValueError)                                   */
+#define SCRIBE_E_LENGTH    2  /* "Lists should have same length" (-> AssertionError)            */
+#define SCRIBE_E_CUDA      3  /* CUDA runtime failure / no device (-> RuntimeError)             */
+#define SCRIBE_E_DOMAIN    4  /* umi hit log(0): reference raises ValueError("math domain error")*/
+#define SCRIBE_E_STATE     5  /* e.g. jobs submitted before a matrix was uploaded                */
+
+/* estimators: Scribe/information_estimators.py mi :59, cmi :111, umi :209, cumi :326 */
+#define SCRIBE_EST_MI    0
+#define SCRIBE_EST_CMI   1
+#define SCRIBE_EST_UMI   2
+#define SCRIBE_EST_CUMI  3
+
+/* density_estimation_method of umi/cumi (information_estimators.py:247-259, :384-394) */
+#define SCRIBE_DENSITY_KDE 0
+#define SCRIBE_DENSITY_KNN 1
+
+/* kernel path selection (testing / debugging) */
+#define SCRIBE_PATH_AUTO    0  /* fused register-top-k kernels when an instantiation exists       */
+#define SCRIBE_PATH_GENERIC 1  /* runtime-dimension kernels (any dx,dy,dz,k within the limits)     */
+
+typedef struct scribe_handle scribe_handle;
+
+typedef struct scribe_opts {
+    int32_t estimator;   /* SCRIBE_EST_*                                                        */
+    int32_t k;           /* neighbours (reference default 5; the drivers never override it)     */
+    int32_t density;     /* SCRIBE_DENSITY_* (umi / cumi only)                                  */
+    int32_t k_density;   /* k of the kNN density estimate                                       */
+    int32_t path;        /* SCRIBE_PATH_*                                                       */
+    int32_t reserved;
+    double  bw;          /* KDE bandwidth in data units (reference default 0.01)                */
+} scribe_opts;
+
+/* One lagged-embedding job = one call of cmi/cumi made by causal_model.rdi (causal_network.py:145-176)
+ * or causal_model.crdi (causal_network.py:257-283).
+ *   n_cond == 0 : RDI(src -> dst, delay):  x = e_src[t], z = e_dst[t+delay-1], y = e_dst[t+delay]
+ *   n_cond == L : cRDI: tau = max(delay, cond_delay[]); x = e_src[t+tau-delay], y = e_dst[t+tau],
+ *                 z = [ e_cond[L-1][t+tau-cond_delay[L-1]], ..., e_cond[0][..], e_dst[t+tau-1] ]
+ * per run, runs concatenated in upload order. */
+typedef struct scribe_job {
+    int32_t src, dst, delay, n_cond;
+    int32_t cond_gene[SCRIBE_MAX_COND];
+    int32_t cond_delay[SCRIBE_MAX_COND];
+} scribe_job;
+
+typedef struct scribe_stats {
+    int64_t kernel_launches;   /* kernels launched by the last compute call                     */
+    int64_t estimator_launches;/* ... of which the O(N^2) estimator kernels                      */
+    double  estimator_ms;      /* device time of those estimator kernels (CUDA events, own stream)*/
+    double  total_ms;          /* device time of the whole call incl. copies                     */
+    int64_t point_pairs;       /* sum over jobs of N^2 (dense point pairs the estimator visited) */
+    int64_t jobs;              /* jobs evaluated                                                 */
+    int64_t h2d_bytes, d2h_bytes;
+} scribe_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int  scribe_abi_version(void);
+const char* scribe_last_error(void);
+/* device < 0 : current device.  Fails with SCRIBE_E_CUDA when no CUDA device is usable. */
+int  scribe_create(int device, scribe_handle** out);
+void scribe_destroy(scribe_handle* h);
+int  scribe_device_info(scribe_handle* h, int32_t* sm_count, int32_t* clock_khz, int64_t* mem_bytes,
+                        char* name, int32_t name_len);
+int  scribe_get_stats(scribe_handle* h, scribe_stats* out);
+
+/* ---- estimator level: replaces a single call of information_estimators.mi/cmi/umi/cumi -------- */
+/* x: dx*n, y: dy*n, z: dz*n doubles (z == NULL and dz == 0 for mi/umi), already normalised by the caller
+ * when the reference's normalization=True is wanted (x/np.std(x), information_estimators.py:150-153). */
+int scribe_estimate(scribe_handle* h, const double* x, const double* y, const double* z,
+                    int64_t n, int32_t dx, int32_t dy, int32_t dz, const scribe_opts* opts, double* out);
+
+/* Debug / bit-exactness entry point: the per-point quantities behind scribe_estimate.
+ *   eps[n]        k-th neighbour distance (information_estimators.py:101,:165,:263,:396)
+ *   counts[4*n]   ball sizes minus self: cmi/cumi {xyz,xz,yz,z}; mi {xy,x,y,(n-1)}; umi {-,x,y,-}
+ *   wsum[2*n]     cumi {W_yz - w_i, W_z - w_i}; umi {W_y - w_i, unused}   (may be NULL)
+ *   weights[n]    uniformisation weights w_i (umi/cumi)                   (may be NULL)      */
+int scribe_debug_counts(scribe_handle* h, const double* x, const double* y, const double* z,
+                        int64_t n, int32_t dx, int32_t dy, int32_t dz, const scribe_opts* opts,
+                        double* eps, int32_t* counts, double* wsum, double* weights);
+
+/* ---- driver level: causal_model.rdi / .crdi (causal_network.py:112-289) ----------------------- */
+/* E: n_genes rows of n_cells doubles (gene-major), NaN padding already removed; run r occupies
+ * columns [run_offsets[r], run_offsets[r+1]) of every row.  Replaces model.expression for the loops
+ * at causal_network.py:140-176 / :223-283.  The matrix stays resident until the next upload. */
+int scribe_upload_matrix(scribe_handle* h, const double* E, int64_t n_genes, int64_t n_cells,
+                         const int64_t* run_offsets, int32_t n_runs);
+/* Evaluate jobs against the resident matrix.  opts->estimator is CMI (uniformization=False) or CUMI.
+ * differential != 0: y = e_dst[p-1] - e_dst[p] (causal_network.py:153,:173).
+ * scales: NULL, or 3 doubles per job {sx, sy, sz}; each role is divided by its scale (the caller computes
+ * np.std for normalization=True).  out: n_jobs doubles, host (…_jobs) or device (…_jobs_dev). */
+int scribe_lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
+                       int32_t differential, const double* scales, double* out_host);
+int scribe_lagged_jobs_dev(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
+                           int32_t differential, const double* scales, double* out_dev);
+
+/* ---- driver level: causal_net_dynamics_coupling (Scribe.py:110-135) --------------------------- */
+/* S, Y: n_genes rows of n_cells doubles.  S = normalised t0 layer (x and z columns, Scribe.py:119,:123);
+ * Y = the y column per gene (S + V when t1_key == 'velocity', else V; Scribe.py:121). */
+int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, int64_t n_genes, int64_t n_cells);
+/* job j: I(S[src[j]] ; Y[dst[j]] | S[dst[j]]); drop_zero_cells keeps cells with (x + y) + z > 0
+ * (Scribe.py:125-128).  n_eff (may be NULL) receives the cells kept per job. */
+int scribe_coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs,
+                         int32_t drop_zero_cells, const scribe_opts* opts, double* out_host, int32_t* n_eff);
+int scribe_coupling_jobs_dev(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs,
+                             int32_t drop_zero_cells, const scribe_opts* opts, double* out_dev, int32_t* n_eff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRIBE_B200_H */

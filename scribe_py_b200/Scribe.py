@@ -1,0 +1,133 @@
+"""Drop-in for Scribe/Scribe.py: `causal_net_dynamics_coupling` (Scribe.py:10-139), plus CLR / check_symmetric.
+
+AnnData in, `adata.uns['causal_net'] = {'RDI': DataFrame}` out.  The per-pair Python loop of the reference
+(Scribe.py:110-135) becomes one batched submission: both layers are normalised with the same pandas
+expressions, uploaded once, and every (TF, target) pair -- zero-cell mask, compaction and cmi -- is evaluated
+on the GPU(s).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+from scipy.sparse import issparse
+
+from . import _lib
+from . import distributed as _dist
+
+CLR_DDOF = 1
+
+__all__ = ["causal_net_dynamics_coupling", "CLR", "check_symmetric"]
+
+
+def _layer_frame(adata, genes, key):
+    sub = adata[:, genes]
+    mat = sub.layers[key]
+    if issparse(mat):
+        mat = mat.todense()
+    df = pd.DataFrame(np.asarray(mat))
+    df.index = adata.obs_names
+    df.columns = sub.var_names
+    return df
+
+
+def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None, t0_key='spliced', t1_key='velocity',
+                                 normalize=True, drop_zero_cells=True, copy=False):
+    """Infer a causal network from dynamics-coupled single-cell measurements: for every TF g_a and target g_b,
+    I(spliced[g_a]; y[g_b] | spliced[g_b]) with y = spliced + velocity when t1_key == 'velocity', else the
+    t1 layer itself.  Arguments and result are those of the reference (Scribe.py:10-64)."""
+    if TFs is None:
+        TFs = adata.var_names.tolist()
+    else:
+        TFs = adata.var_names.intersection(TFs).tolist()
+        if len(TFs) == 0:
+            raise Exception("The adata object has no gene names from .var_name that intersects with the TFs list you provided")
+    if Targets is None:
+        Targets = adata.var_names.tolist()
+    else:
+        Targets = adata.var_names.intersection(Targets).tolist()
+        if len(Targets) == 0:
+            raise Exception("The adata object has no gene names from .var_name that intersect with the Targets list you provided")
+
+    if guide_keys is not None:                       # computed and unused, as in the reference (Scribe.py:80-86)
+        guides = np.unique(adata.obs[guide_keys].tolist())
+        guides = np.setdiff1d(guides, ['*', 'nan', 'neg'])
+
+    genes = np.unique(TFs + Targets)
+    spliced = _layer_frame(adata, genes, t0_key)
+    velocity = _layer_frame(adata, genes, t1_key)
+    velocity[pd.isna(velocity)] = 0
+    if normalize:                                    # Scribe.py:104-106, same pandas expressions
+        spliced = (spliced - spliced.mean()) / (spliced.max() - spliced.min())
+        velocity = (velocity - velocity.mean()) / (velocity.max() - velocity.min())
+    y = (spliced + velocity) if t1_key == 'velocity' else velocity            # Scribe.py:121
+
+    col = {g: i for i, g in enumerate(spliced.columns)}
+    S = np.ascontiguousarray(spliced.to_numpy(dtype=np.float64).T)
+    Y = np.ascontiguousarray(y.to_numpy(dtype=np.float64).T)
+    ia = np.array([col[g] for g in TFs], dtype=np.int32)
+    ib = np.array([col[g] for g in Targets], dtype=np.int32)
+    # job order: target-major so a rank's slab shares y/z columns
+    bb, aa = np.meshgrid(np.arange(len(Targets)), np.arange(len(TFs)), indexing="ij")
+    names_differ = np.array([[TFs[a] != Targets[b] for a in range(len(TFs))] for b in range(len(Targets))])
+    aa, bb = aa[names_differ], bb[names_differ]
+    src, dst = ia[aa], ib[bb]
+
+    h = _lib.default_handle()
+    h.upload_coupling(S, Y)
+    opts = _lib.make_opts(_lib.EST_CMI, 5)
+
+    def evaluate(lo, hi):
+        return h.coupling_jobs(src[lo:hi], dst[lo:hi], opts, drop_zero_cells)
+
+    vals = _dist.sharded_evaluate(len(src), evaluate)
+    M = np.full((len(TFs), len(Targets)), np.nan)
+    M[aa, bb] = vals
+    causal_net = pd.DataFrame(M, index=TFs, columns=Targets)
+    adata.uns['causal_net'] = {"RDI": causal_net.fillna(0)}
+    return adata if copy else None
+
+
+def CLR(causality_mat, zscore_both_dim=None):
+    """Context likelihood of relatedness of a causality matrix (Scribe.py:142-176)."""
+    zscore_both_dim = check_symmetric(causality_mat) if zscore_both_dim is None else zscore_both_dim
+    if isinstance(causality_mat, pd.DataFrame):
+        mat = causality_mat.values
+    elif issparse(causality_mat):
+        mat = causality_mat.toarray()
+    else:
+        mat = causality_mat
+    square = mat.shape[0] == mat.shape[1]
+
+    def zscore(axis):
+        z = np.round(mat, 10)
+        mu = np.mean(mat, axis=axis)
+        sd = np.std(mat, axis=axis, ddof=CLR_DDOF)
+        if not square:
+            mu = mu[:, None] if axis == 1 else mu[None, :]
+            sd = sd[:, None] if axis == 1 else sd[None, :]
+        z = np.divide(np.subtract(z, mu), sd)
+        z[z < 0] = 0
+        return z
+
+    z_row = zscore(1)
+    if zscore_both_dim:
+        z_col = zscore(0)
+        res = np.sqrt((np.square(z_row) + np.square(z_col)) / 2)
+    else:
+        res = np.sqrt(np.square(z_row))
+    if isinstance(causality_mat, pd.DataFrame):
+        res = pd.DataFrame(res)
+        res.index, res.columns = causality_mat.index, causality_mat.columns
+    return res
+
+
+def check_symmetric(a, rtol=1e-05, atol=1e-08):
+    """(Scribe.py:179-192)"""
+    if a.shape[0] != a.shape[1]:
+        return False
+    if isinstance(a, pd.DataFrame):
+        a = a.fillna(-1).values
+    if issparse(a):
+        a.data = np.nan_to_num(a.data)
+        return (abs(a - a.T) > atol).nnz == 0
+    return np.allclose(a, a.T, rtol=rtol, atol=atol)

@@ -1,0 +1,322 @@
+"""Drop-in for Scribe/causal_network.py: the `causal_model` class.
+
+`rdi` and `crdi` keep the reference's signatures and return types (causal_network.py:112-187, :190-289) but
+instead of calling cmi/cumi once per ordered pair and delay they pack every (source, target, delay) job of
+the call into one batched submission to the CUDA library (one upload of the expression matrix, lagged
+columns materialised once per (gene, shift) and shared by all pairs that read them), sharded across the
+GPUs of the box when torch.distributed is initialised.
+
+Behaviours of the reference that crash on a current numpy/pandas stack (np.int at :299, the single-run
+cRDI concatenation at :246, the Pool branch at :158/:181) are made to work here with the semantics of the
+branches that do run (multi-run cRDI, :257-283).
+"""
+from __future__ import annotations
+
+import warnings
+from copy import deepcopy
+
+import numpy as np
+import pandas as pd
+
+from . import _lib
+from . import distributed as _dist
+
+__all__ = ["causal_model"]
+
+
+class causal_model(object):
+    """Holds gene expression (genes x cells, single-run index GENE_ID or MultiIndex (GENE_ID, RUN_ID)) and
+    computes pairwise RDI / cRDI scores on the GPU."""
+
+    def __init__(self, expression=None):
+        if expression is None:
+            warnings.warn(" WARNING: No expression data argument given. if you intend to load the data from a file, "
+                          "call the method 'read_expression_file'.")
+        else:
+            self.expression = deepcopy(expression)
+            self.expression_raw = expression
+            if isinstance(expression, pd.DataFrame):
+                if expression.index.nlevels == 1:
+                    self.node_ids = expression.index
+                else:
+                    self.node_ids = expression.index.levels[0]
+                    self.run_ids = expression.index.levels[1]
+        self.rdi_results = None
+        self.crdi_results = None
+
+    # ------------------------------------------------------------------ I/O and preprocessing (pass-through)
+    def read_expression_file(self, expression_path, data_mode, verbose=False, genotype_path=None, phenotype_path=None):
+        """Tab-separated expression table -> DataFrame (causal_network.py:28-65)."""
+        if verbose:
+            print("\nLoading data... ",)
+        if data_mode == "single_run":
+            self.expression = pd.read_table(expression_path, delimiter="\t", header=0, index_col="GENE_ID")
+            self.expression_raw = deepcopy(self.expression)
+            self.node_ids = self.expression.index
+            self.expression_concatenated = self.expression
+        elif data_mode == "multi_run":
+            self.expression = pd.read_table(expression_path, delimiter="\t", header=0, index_col=["GENE_ID", "RUN_ID"])
+            self.expression_raw = deepcopy(self.expression)
+            self.node_ids = self.expression.index.levels[0]
+            self.run_ids = self.expression.index.levels[1]
+            self.expression_concatenated = pd.concat(
+                [pd.DataFrame(self.expression.loc[g].values.reshape(1, -1), index=[g]) for g in self.node_ids])
+        else:
+            raise ValueError("Data mode invalid")
+        if verbose:
+            print("DONE.")
+            if data_mode == "single_run":
+                print("A total number of", self.expression.shape[0], "genes, each containing",
+                      self.expression.shape[1], "pseudo-times were read.\n")
+            else:
+                print("A total number of", len(self.expression.index.levels[0]), "genes, each gene containing",
+                      len(self.expression.index.levels[1]), "runs and each run containing at most",
+                      self.expression.shape[1], "pseudo-times were read.\n")
+
+    def restore_the_raw_expression_data(self):
+        self.expression = deepcopy(self.expression_raw)
+
+    def subset_genes(self, subset):
+        if self.expression.index.nlevels == 1:
+            self.expression = self.expression.loc[subset, :]
+        else:
+            keep = [ix for ix in self.expression.index if ix[0] in subset]
+            self.expression = self.expression.loc[keep, :]
+        self.node_ids = subset
+
+    def subset_runs(self, subset):
+        if self.expression.index.nlevels == 1:
+            warnings.warn("WARNING: Cannot perform run-subsetting on a single-run mode data.")
+        else:
+            keep = [ix for ix in self.expression.index if ix[1] in subset]
+            self.expression = self.expression.loc[keep, :]
+            self.expression_concatenated = pd.concat(
+                [pd.DataFrame(self.expression.loc[g].values.reshape(1, -1), index=[g]) for g in self.node_ids])
+            self.run_ids = subset
+
+    def smooth(self, window):
+        """Rolling mean along the cell axis (causal_network.py:97-101; written without the removed axis= kwarg)."""
+        sm = self.expression_raw.T.rolling(window=window).mean().T
+        self.expression = sm.dropna(axis=1, how="all")
+
+    def normalize(self):
+        """z-score every row, NaN -> 0 (causal_network.py:104-109)."""
+        e = self.expression.sub(self.expression.mean(axis=1), axis=0)
+        e = e.div(self.expression.std(axis=1), axis=0)
+        self.expression = e.fillna(0)
+
+    # ------------------------------------------------------------------ dense layout for the device
+    def _dense(self):
+        """(node_ids list, E genes x cells float64 with NaN dropped, run_offsets int64).
+
+        Mirrors `.loc[gene(, run)].dropna()` (causal_network.py:147,:167): NaNs are removed per gene and run;
+        all genes must then agree on every run length, otherwise the reference's cmi would fail its
+        "Lists should have same length" assertion."""
+        node_ids = list(self.node_ids)
+        expr = self.expression
+        if expr.index.nlevels == 1:
+            runs = [None]
+        else:
+            runs = list(self.run_ids)
+        blocks, lengths = [], []
+        for run in runs:
+            if run is None:
+                vals = expr.loc[node_ids].to_numpy(dtype=np.float64)
+            else:
+                vals = expr.loc[[(g, run) for g in node_ids]].to_numpy(dtype=np.float64)
+            ok = ~np.isnan(vals)
+            cnt = ok.sum(axis=1)
+            assert (cnt == cnt[0]).all(), "Lists should have same length"
+            T = int(cnt[0])
+            if ok.all():
+                blk = vals
+            elif (ok == ok[0]).all():
+                blk = vals[:, ok[0]]
+            else:
+                blk = np.stack([vals[g][ok[g]] for g in range(len(node_ids))])
+            blocks.append(blk)
+            lengths.append(T)
+        E = np.ascontiguousarray(np.concatenate(blocks, axis=1))
+        run_off = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
+        return node_ids, E, run_off
+
+    @staticmethod
+    def _lag_std(E, run_off, delays):
+        """np.std of the x / y(differential) / z columns per (gene, delay) for normalization=True
+        (information_estimators.py:150-153 applied to the slices of causal_network.py:147-153)."""
+        G = E.shape[0]
+        out = {}
+        for d in delays:
+            sx = np.empty(G); sy = np.empty(G); sz = np.empty(G)
+            for g in range(G):
+                xs, ys, zs = [], [], []
+                for r in range(len(run_off) - 1):
+                    e = E[g, run_off[r]:run_off[r + 1]]
+                    T = len(e)
+                    if T <= d:
+                        continue
+                    xs.append(e[:T - d]); zs.append(e[d - 1:T - 1]); ys.append(e[d - 1:T - 1] - e[d:T])
+                sx[g] = np.std(np.concatenate(xs)[:, None]); sy[g] = np.std(np.concatenate(ys)[:, None])
+                sz[g] = np.std(np.concatenate(zs)[:, None])
+            out[d] = (sx, sy, sz)
+        return out
+
+    def _frame(self, M, node_ids):
+        return pd.DataFrame(M, index=node_ids, columns=node_ids)
+
+    # ------------------------------------------------------------------ RDI
+    def rdi(self, delays, number_of_processes=1, uniformization=False, differential_mode=False):
+        """Pairwise Restricted Directed Information for every delay in `delays` (causal_network.py:112-187).
+
+        Returns (and stores in self.rdi_results) {delay: G x G DataFrame (rows = source, columns = target,
+        NaN diagonal)} plus "MAX", the element-wise maximum over delays (-inf diagonal).
+        `number_of_processes` is accepted and ignored: parallelism comes from the GPU(s)."""
+        delays = list(delays)
+        node_ids, E, run_off = self._dense()
+        G = len(node_ids)
+        h = _lib.default_handle()
+        h.upload_matrix(E, run_off)
+
+        # job order: delay-major, then target, then source (a rank's slab shares target columns)
+        tgt, src = np.meshgrid(np.arange(G, dtype=np.int32), np.arange(G, dtype=np.int32), indexing="ij")
+        off = tgt != src
+        tgt, src = tgt[off], src[off]
+        per = len(tgt)
+        jobs = np.zeros(per * len(delays), dtype=_lib.JOB_DTYPE)
+        for i, d in enumerate(delays):
+            sl = slice(i * per, (i + 1) * per)
+            jobs["src"][sl] = src; jobs["dst"][sl] = tgt; jobs["delay"][sl] = int(d)
+        scales = None
+        if differential_mode:
+            st = self._lag_std(E, run_off, delays)
+            scales = np.empty((len(jobs), 3))
+            for i, d in enumerate(delays):
+                sl = slice(i * per, (i + 1) * per)
+                sx, sy, sz = st[d]
+                scales[sl, 0] = sx[src]; scales[sl, 1] = sy[tgt]; scales[sl, 2] = sz[tgt]
+        opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
+
+        def evaluate(lo, hi):
+            return h.lagged_jobs(jobs[lo:hi], opts, differential_mode, None if scales is None else scales[lo:hi])
+
+        vals = _dist.sharded_evaluate(len(jobs), evaluate)
+        self.rdi_results = {}
+        for i, d in enumerate(delays):
+            M = np.full((G, G), np.nan)
+            M[src, tgt] = vals[i * per:(i + 1) * per]
+            self.rdi_results[d] = self._frame(M, node_ids)
+        self.rdi_results["MAX"] = self.__extract_max_rdi_value_delay()[0]
+        return self.rdi_results
+
+    # ------------------------------------------------------------------ cRDI
+    def crdi(self, L=1, number_of_processes=1, uniformization=False, differential_mode=False):
+        """Conditional RDI given the top-L other incoming regulators of each target (causal_network.py:190-289)."""
+        if self.rdi_results is None:
+            warnings.warn("WARNING: The method first needs RDI to be run, RUNNING RDI NOW... delay set to [1]")
+            self.rdi(delays=[1], number_of_processes=number_of_processes, uniformization=uniformization,
+                     differential_mode=differential_mode)
+        if L > _lib.MAX_COND:
+            raise ValueError("crdi supports at most %d conditioning genes" % _lib.MAX_COND)
+        node_ids, E, run_off = self._dense()
+        G = len(node_ids)
+        pos = {g: i for i, g in enumerate(node_ids)}
+        max_val, max_delay = self.__extract_max_rdi_value_delay()
+        top_nodes, top_delays, top_values = self.__extract_top_incoming_nodes_delays(max_val, max_delay, k_nodes=L)
+
+        mv = max_delay.to_numpy()
+        jobs = np.zeros(G * (G - 1), dtype=_lib.JOB_DTYPE)
+        j = 0
+        for a_i, a in enumerate(node_ids):
+            for b_i, b in enumerate(node_ids):
+                if a_i == b_i:
+                    continue
+                nodes = list(top_nodes[b]); dls = list(top_delays[b])
+                if a in top_nodes[b]:                                   # causal_network.py:230-232
+                    drop = top_nodes[b].index(a)
+                else:                                                   # :233-235, first minimal slot
+                    drop = top_values[b].index(min(top_values[b]))
+                del nodes[drop]; del dls[drop]
+                if any(n is None for n in nodes):
+                    raise ValueError("crdi needs at least L+1 scored incoming regulators per target")
+                jobs["src"][j] = a_i; jobs["dst"][j] = b_i; jobs["delay"][j] = int(mv[a_i, b_i]); jobs["n_cond"][j] = L
+                for c in range(L):
+                    jobs["cond_gene"][j, c] = pos[nodes[c]]; jobs["cond_delay"][j, c] = int(dls[c])
+                j += 1
+        h = _lib.default_handle()
+        h.upload_matrix(E, run_off)
+        opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
+        scales = None
+        if differential_mode:
+            raise NotImplementedError("differential_mode cRDI has no runnable reference (causal_network.py:250,:271 "
+                                      "slice one element too many)")
+
+        def evaluate(lo, hi):
+            return h.lagged_jobs(jobs[lo:hi], opts, False, scales)
+
+        vals = _dist.sharded_evaluate(len(jobs), evaluate)
+        M = np.full((G, G), np.nan)
+        M[jobs["src"], jobs["dst"]] = vals
+        self.crdi_results = self._frame(M, node_ids)
+        return self.crdi_results
+
+    # ------------------------------------------------------------------ reductions over the RDI matrices
+    def __extract_max_rdi_value_delay(self):
+        """Max over delays and the delay attaining it; strict '>' so the first delay wins ties, the diagonal
+        keeps -inf / NaN (causal_network.py:295-311, without the removed np.int)."""
+        node_ids = list(self.node_ids)
+        G = len(node_ids)
+        val = np.full((G, G), -np.inf)
+        arg = np.full((G, G), np.nan, dtype=object)
+        for delay, frame in self.rdi_results.items():
+            if isinstance(delay, str) and delay == "MAX":
+                continue
+            M = frame.loc[node_ids, node_ids].to_numpy(dtype=np.float64)
+            better = M > val
+            np.fill_diagonal(better, False)
+            val[better] = M[better]
+            arg[better] = delay
+        return self._frame(val, node_ids), pd.DataFrame(arg, index=node_ids, columns=node_ids, dtype=object)
+
+    def __extract_top_incoming_nodes_delays(self, max_rdi_values, max_rdi_delays, k_nodes):
+        """Per target the k_nodes+1 strongest sources by streaming replace-first-minimum
+        (causal_network.py:316-333)."""
+        node_ids = list(self.node_ids)
+        V = max_rdi_values.loc[node_ids, node_ids].to_numpy(dtype=np.float64)
+        Dl = max_rdi_delays.loc[node_ids, node_ids].to_numpy()
+        top_nodes, top_delays, top_values = {}, {}, {}
+        for b_i, b in enumerate(node_ids):
+            nodes = [None] * (k_nodes + 1); dls = [np.nan] * (k_nodes + 1); vals = [-np.inf] * (k_nodes + 1)
+            col = V[:, b_i]
+            for a_i, a in enumerate(node_ids):
+                if a_i == b_i:
+                    continue
+                lo = min(vals)
+                if col[a_i] > lo:
+                    s = vals.index(lo)
+                    nodes[s] = a; dls[s] = Dl[a_i, b_i]; vals[s] = col[a_i]
+            top_nodes[b], top_delays[b], top_values[b] = nodes, dls, vals
+        return top_nodes, top_delays, top_values
+
+    # ------------------------------------------------------------------ evaluation (pass-through)
+    def roc(self, results, true_graph_path):
+        """ROC curve and AUROC of a score matrix against an edge list file (causal_network.py:337-389)."""
+        with open(true_graph_path) as fh:
+            true_edges = set(line.strip().lower() for line in fh)
+        scored = []
+        for a in self.node_ids:
+            for b in self.node_ids:
+                if a == b:
+                    continue
+                scored.append((a.lower() + "\t" + b.lower(), results.loc[a, b]))
+        order = [e for e, _ in sorted(scored, key=lambda t: t[1], reverse=True)]
+        fp, tp = [0], [0]
+        for e in order:
+            hit = e in true_edges
+            tp.append(tp[-1] + (1 if hit else 0))
+            fp.append(fp[-1] + (0 if hit else 1))
+        x = [v / float(max(fp)) for v in fp]
+        y = [v / float(max(tp)) for v in tp]
+        auroc = 0
+        for i in range(1, len(x)):
+            auroc += abs((x[i] - x[i - 1]) * (y[i] + y[i - 1]) / 2)
+        return auroc, x, y

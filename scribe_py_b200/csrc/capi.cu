@@ -1,0 +1,631 @@
+// capi.cu -- host side of libscribe_b200.so: handle, workspaces, job batching and the extern "C" boundary
+// declared in include/scribe_b200.h.  No torch types, no CPU compute path: without a CUDA device every
+// entry point fails.
+#include "../../include/scribe_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace scribe;
+
+static thread_local std::string g_err;
+extern "C" const char* scribe_last_error(void) { return g_err.c_str(); }
+extern "C" int scribe_abi_version(void) { return SCRIBE_ABI_VERSION; }
+
+namespace {
+
+struct Fail { int code; std::string msg; };
+[[noreturn]] void fail(int code, const std::string& m) { throw Fail{code, m}; }
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    fail(SCRIBE_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&p, want)); cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct scribe_handle {
+    int device = 0;
+    int sm_count = 0, clock_khz = 0;
+    size_t mem_bytes = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    // resident inputs
+    DevBuf E, run_off_d; int64_t n_genes = 0, n_cells = 0; std::vector<int64_t> run_off;
+    DevBuf S, Y; int64_t cg = 0, cc = 0;
+    // workspaces
+    DevBuf psi; int psi_n = 0;
+    DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
+    scribe_stats st{};
+    size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
+};
+
+namespace {
+
+struct Guard {   // selects the handle's device for the duration of a call
+    int prev = -1;
+    explicit Guard(scribe_handle* h) { cudaGetDevice(&prev); cudaSetDevice(h->device); }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void ensure_psi(scribe_handle* h, int n_max) {
+    if (n_max + 2 <= h->psi_n) return;
+    const int m = std::max(n_max + 2, 4096);
+    std::vector<double> t(m);
+    for (int i = 0; i < m; i++) t[i] = digamma_f64((double)i);      // psi(0) = -inf like scipy
+    h->psi.ensure(sizeof(double) * m);
+    CU(cudaMemcpyAsync(h->psi.p, t.data(), sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->st.h2d_bytes += sizeof(double) * m;
+    h->psi_n = m;
+}
+
+void check_opts(const scribe_opts* o) {
+    if (!o) fail(SCRIBE_E_ARG, "opts is NULL");
+    if (o->estimator < 0 || o->estimator > 3) fail(SCRIBE_E_ARG, "unknown estimator");
+    if (o->k < 1 || o->k > SCRIBE_MAX_K) fail(SCRIBE_E_ARG, "k must be in [1, 63]");
+    if (o->estimator >= SCRIBE_EST_UMI) {
+        if (o->density != SCRIBE_DENSITY_KDE && o->density != SCRIBE_DENSITY_KNN)
+            fail(SCRIBE_E_ARG, "The density estimation method is not recognized");
+        if (o->density == SCRIBE_DENSITY_KNN && (o->k_density < 1 || o->k_density > SCRIBE_MAX_K))
+            fail(SCRIBE_E_ARG, "k_density must be in [1, 63]");
+        if (o->density == SCRIBE_DENSITY_KDE && !(o->bw > 0.0)) fail(SCRIBE_E_ARG, "bw must be positive");
+    }
+}
+
+// ---- fused-kernel dispatch -------------------------------------------------------------------------
+using FusedFn = void (*)(const JobDesc*, int, int, int, const double*, double*, PointOut);
+
+template <int DX, int DY, int DZ, bool W>
+FusedFn pick_kq(int kcap, int q) {
+    if (kcap == 6)  return q == 1 ? ksg_fused_kernel<DX, DY, DZ, 6, 1, W>  : ksg_fused_kernel<DX, DY, DZ, 6, 2, W>;
+    if (kcap == 16) return q == 1 ? ksg_fused_kernel<DX, DY, DZ, 16, 1, W> : ksg_fused_kernel<DX, DY, DZ, 16, 2, W>;
+    return nullptr;
+}
+
+FusedFn pick_fused(int dx, int dy, int dz, int kcap, int q, bool weighted) {
+    if (dx != 1 || dy != 1) return nullptr;
+    if (!weighted) {
+        switch (dz) {
+            case 0: return pick_kq<1, 1, 0, false>(kcap, q);
+            case 1: return pick_kq<1, 1, 1, false>(kcap, q);
+            case 2: return pick_kq<1, 1, 2, false>(kcap, q);
+            case 3: return pick_kq<1, 1, 3, false>(kcap, q);
+        }
+    } else {
+        switch (dz) {
+            case 1: return pick_kq<1, 1, 1, true>(kcap, q);
+            case 2: return pick_kq<1, 1, 2, true>(kcap, q);
+            case 3: return pick_kq<1, 1, 3, true>(kcap, q);
+        }
+    }
+    return nullptr;
+}
+
+using KdeFn = void (*)(const JobDesc*, int, const int*, double, double*);
+KdeFn pick_kde(int dp) {
+    switch (dp) {
+        case 1: return kde_kernel<1, 2>;
+        case 2: return kde_kernel<2, 2>;
+        case 3: return kde_kernel<3, 2>;
+        case 4: return kde_kernel<4, 2>;
+        case 5: return kde_kernel<5, 2>;
+        case 6: return kde_kernel<6, 2>;
+    }
+    return nullptr;
+}
+
+struct DebugPtrs { double* eps = nullptr; int32_t* cnt = nullptr; double* wsum = nullptr; double* weights = nullptr; };
+
+// Evaluate `hj.size()` jobs whose columns are already in device memory.  out_dev: one double per job.
+// dbg (optional, single-chunk only): host pointers that receive the per-point quantities of job 0..n-1.
+void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int dy, int dz,
+              const scribe_opts* o, double* out_dev, bool n_on_device, const DebugPtrs* dbg, bool* domain_error)
+{
+    const int64_t nj = (int64_t)hj.size();
+    if (nj == 0) return;
+    const int est = o->estimator;
+    const int D = dx + dy + dz;
+    if (dx < 1 || dy < 1 || dz < 0 || D > SCRIBE_MAX_DIM) fail(SCRIBE_E_ARG, "unsupported dimensions (need dx,dy >= 1, dx+dy+dz <= 16)");
+    if ((est == SCRIBE_EST_MI || est == SCRIBE_EST_UMI) && dz != 0) fail(SCRIBE_E_ARG, "mi/umi take no conditioning variable");
+    if ((est == SCRIBE_EST_CMI || est == SCRIBE_EST_CUMI) && dz < 1) fail(SCRIBE_E_ARG, "cmi/cumi need a conditioning variable");
+    const bool weighted = est >= SCRIBE_EST_UMI;
+    const bool euclid = est == SCRIBE_EST_UMI;
+    ensure_psi(h, n_max);
+
+    const int k = o->k;
+    const int kcap = (k + 1 <= 6) ? 6 : ((k + 1 <= 16) ? 16 : 0);
+    const int q = (n_max > 2 * TPB) ? 2 : 1;
+    FusedFn fused = nullptr;
+    if (o->path == SCRIBE_PATH_AUTO && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
+    const bool need_points = (fused == nullptr) || dbg != nullptr;
+
+    for (int64_t j = 0; j < nj; j++) hj[j].qoff = j * (int64_t)n_max;
+    const int bpj_f = (n_max + TPB * q - 1) / (TPB * q);       // CTAs per job, fused
+    const int bpj_1 = (n_max + TPB - 1) / TPB;                  // CTAs per job, one query per thread
+    const int bpj_kde = (n_max + TPB * 2 - 1) / (TPB * 2);
+    if (nj * (int64_t)std::max(bpj_f, bpj_1) > 2000000000LL) fail(SCRIBE_E_ARG, "too many CTAs in one chunk");
+
+    h->jobs.ensure(sizeof(JobDesc) * nj);
+    JobDesc* dj = h->jobs.as<JobDesc>();
+    if (n_on_device) {
+        // column pointers were produced on the host but n lives in the device copy (coupling prep wrote it):
+        // only refresh pointers by a second pass below; here the caller has already uploaded descs.
+    } else {
+        CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
+        h->st.h2d_bytes += sizeof(JobDesc) * nj;
+    }
+
+    PointOut po{nullptr, nullptr, nullptr};
+    if (need_points) {
+        h->eps.ensure(sizeof(double) * nj * n_max);
+        h->cnt.ensure(sizeof(int32_t) * 4 * nj * n_max);
+        po.eps = h->eps.as<double>(); po.cnt = h->cnt.as<int32_t>();
+        if (weighted) { h->wsum.ensure(sizeof(double) * 2 * nj * n_max); po.wsum = h->wsum.as<double>(); }
+        if (dbg) {   // make untouched slots recognisable
+            CU(cudaMemsetAsync(po.cnt, 0xff, sizeof(int32_t) * 4 * nj * n_max, h->stream));
+        }
+    }
+
+    CU(cudaEventRecord(h->ev_k0, h->stream));
+    // ---- uniformisation weights -------------------------------------------------------------------
+    if (weighted) {
+        h->u.ensure(sizeof(double) * nj * n_max);
+        double* u = h->u.as<double>();
+        std::vector<int> pd;                                    // dims of P: x (umi) or x|z (cumi)
+        for (int c = 0; c < dx; c++) pd.push_back(c);
+        if (est == SCRIBE_EST_CUMI) for (int c = 0; c < dz; c++) pd.push_back(dx + dy + c);
+        const int dp = (int)pd.size();
+        if (o->density == SCRIBE_DENSITY_KDE) {
+            KdeFn kf = pick_kde(dp);
+            if (!kf) fail(SCRIBE_E_ARG, "KDE supports at most 6 density dimensions");
+            h->dims.ensure(sizeof(int) * MAXD);
+            CU(cudaMemcpyAsync(h->dims.p, pd.data(), sizeof(int) * dp, cudaMemcpyHostToDevice, h->stream));
+            const double scale = std::sqrt(1.4426950408889634 / (2.0 * o->bw * o->bw));
+            kf<<<(unsigned)(nj * bpj_kde), TPB, 0, h->stream>>>(dj, bpj_kde, h->dims.as<int>(), scale, u);
+            CU(cudaGetLastError());
+            h->st.kernel_launches++; h->st.estimator_launches++;
+        } else {
+            // sub-jobs over the density subspace, kNN-only generic kernel, then k/N/r^d
+            if (n_on_device) fail(SCRIBE_E_ARG, "kNN density is not available on the coupling path");
+            std::vector<JobDesc> sub(hj);
+            for (auto& s : sub) { for (int c = 0; c < dp; c++) s.col[c] = hj[&s - sub.data()].col[pd[c]]; s.w = nullptr; }
+            h->pjobs.ensure(sizeof(JobDesc) * nj);
+            CU(cudaMemcpyAsync(h->pjobs.p, sub.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
+            h->r.ensure(sizeof(double) * nj * n_max);
+            PointOut pr{h->r.as<double>(), nullptr, nullptr};
+            ksg_generic_kernel<<<(unsigned)(nj * bpj_1), TPB, 0, h->stream>>>(h->pjobs.as<JobDesc>(), bpj_1, dp, 0, 0,
+                                                                             o->k_density, 0, 1, pr);
+            CU(cudaGetLastError());
+            knn_density_kernel<<<(unsigned)(nj * bpj_1), TPB, 0, h->stream>>>(dj, bpj_1, o->k_density, dp, h->r.as<double>(), u);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(h->stream));               // `sub` must outlive the copy
+            h->st.kernel_launches += 2; h->st.estimator_launches++;
+        }
+        normalize_weights_kernel<<<(unsigned)nj, TPB, 0, h->stream>>>(dj, u);
+        CU(cudaGetLastError());
+        h->st.kernel_launches++;
+        // point every job at its weights
+        if (n_on_device) fail(SCRIBE_E_ARG, "uniformised estimators are not available on the coupling path");
+        for (int64_t j = 0; j < nj; j++) hj[j].w = u + hj[j].qoff;
+        CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+
+    // ---- estimator -----------------------------------------------------------------------------------
+    if (fused) {
+        h->partial.ensure(sizeof(double) * nj * bpj_f);
+        CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * bpj_f, h->stream));
+        const int mode = (est == SCRIBE_EST_MI) ? MODE_MI : MODE_CMI;
+        fused<<<(unsigned)(nj * bpj_f), TPB, 0, h->stream>>>(dj, bpj_f, k, mode, h->psi.as<double>(), h->partial.as<double>(), po);
+        CU(cudaGetLastError());
+        finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), bpj_f, (int)nj, out_dev);
+        CU(cudaGetLastError());
+        h->st.kernel_launches += 2; h->st.estimator_launches++;
+    } else {
+        if (k + 1 > GEN_KCAP) fail(SCRIBE_E_ARG, "k too large");
+        h->flag.ensure(sizeof(int));
+        CU(cudaMemsetAsync(h->flag.p, 0, sizeof(int), h->stream));
+        ksg_generic_kernel<<<(unsigned)(nj * bpj_1), TPB, 0, h->stream>>>(dj, bpj_1, dx, dy, dz, k, euclid ? 1 : 0, 0, po);
+        CU(cudaGetLastError());
+        ksg_finish_kernel<<<(unsigned)nj, TPB, 0, h->stream>>>(dj, est, h->psi.as<double>(), po, out_dev, h->flag.as<int>());
+        CU(cudaGetLastError());
+        h->st.kernel_launches += 2; h->st.estimator_launches++;
+        if (euclid) {
+            int flag = 0;
+            CU(cudaMemcpyAsync(&flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (flag && domain_error) *domain_error = true;
+        }
+    }
+    CU(cudaEventRecord(h->ev_k1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1));
+    h->st.estimator_ms += ms;
+    h->st.jobs += nj;
+
+    if (dbg) {
+        const int n = hj[0].n;
+        if (dbg->eps)  CU(cudaMemcpy(dbg->eps, po.eps, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (dbg->cnt)  CU(cudaMemcpy(dbg->cnt, po.cnt, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost));
+        if (dbg->wsum && weighted) CU(cudaMemcpy(dbg->wsum, po.wsum, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+        if (dbg->weights && weighted) CU(cudaMemcpy(dbg->weights, h->u.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    }
+}
+
+double vd_host(int d) { return 0.5 * d * std::log(3.14159265358979323846) - std::lgamma(0.5 * d + 1.0); }
+
+void begin_call(scribe_handle* h) {
+    std::memset(&h->st, 0, sizeof(h->st));
+    CU(cudaEventRecord(h->ev_call0, h->stream));
+}
+void end_call(scribe_handle* h) {
+    CU(cudaEventRecord(h->ev_call1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev_call0, h->ev_call1));
+    h->st.total_ms = ms;
+}
+
+// single job from host columns (estimator-level entry points)
+void single_job(scribe_handle* h, const double* x, const double* y, const double* z, int64_t n, int dx, int dy, int dz,
+                const scribe_opts* o, double* out, const DebugPtrs* dbg)
+{
+    check_opts(o);
+    if (n < 1) fail(SCRIBE_E_ARG, "need at least one sample");
+    if (n > 2000000) fail(SCRIBE_E_ARG, "n too large for a single job");
+    if (!x || !y || (dz > 0 && !z)) fail(SCRIBE_E_ARG, "NULL input");
+    if (o->estimator == SCRIBE_EST_UMI && !(o->k <= n - 1)) fail(SCRIBE_E_LENGTH, "Set k smaller than num. samples - 1");
+    const int D = dx + dy + dz;
+    if (D > SCRIBE_MAX_DIM || dx < 1 || dy < 1 || dz < 0) fail(SCRIBE_E_ARG, "unsupported dimensions");
+    begin_call(h);
+    h->single.ensure(sizeof(double) * (size_t)D * n + sizeof(double));
+    double* base = h->single.as<double>();
+    CU(cudaMemcpyAsync(base, x, sizeof(double) * dx * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(base + (size_t)dx * n, y, sizeof(double) * dy * n, cudaMemcpyHostToDevice, h->stream));
+    if (dz) CU(cudaMemcpyAsync(base + (size_t)(dx + dy) * n, z, sizeof(double) * dz * n, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += sizeof(double) * D * n;
+    std::vector<JobDesc> hj(1);
+    std::memset(&hj[0], 0, sizeof(JobDesc));
+    for (int c = 0; c < D; c++) hj[0].col[c] = base + (size_t)c * n;
+    hj[0].n = (int)n;
+    h->out.ensure(sizeof(double));
+    bool dom = false;
+    run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom);
+    h->st.point_pairs += n * n;
+    double v = 0.0;
+    CU(cudaMemcpyAsync(&v, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    end_call(h);
+    h->st.d2h_bytes += sizeof(double);
+    if (o->estimator == SCRIBE_EST_UMI) {
+        if (dom) fail(SCRIBE_E_DOMAIN, "math domain error");
+        // information_estimators.py:264,:274-276
+        const double N = (double)n;
+        v = digamma_f64((double)o->k) + 2.0 * std::log(N - 1.0) - digamma_f64(N) + vd_host(dx) + vd_host(dy) - vd_host(dx + dy) - v / N;
+    }
+    if (out) *out = v;
+}
+
+struct ColKey {
+    int32_t gene, shift, tau, diff; uint64_t scale_bits;
+    bool operator==(const ColKey& o) const { return gene == o.gene && shift == o.shift && tau == o.tau && diff == o.diff && scale_bits == o.scale_bits; }
+};
+struct ColKeyHash {
+    size_t operator()(const ColKey& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.gene * 0x9E3779B97F4A7C15ULL;
+        h ^= ((uint64_t)(uint32_t)k.shift << 32 | (uint32_t)k.tau) * 0xC2B2AE3D27D4EB4FULL;
+        h ^= (k.scale_bits + (uint64_t)k.diff) * 0x165667B19E3779F9ULL;
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+
+void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* o, int differential,
+                 const double* scales, double* out, bool out_is_device)
+{
+    check_opts(o);
+    if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) fail(SCRIBE_E_ARG, "lagged jobs use cmi or cumi");
+    if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
+    if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !out))) fail(SCRIBE_E_ARG, "NULL jobs/out");
+    begin_call(h);
+    const int n_runs = (int)h->run_off.size() - 1;
+    // jobs are processed in chunks of equal conditioning-set size (equal joint dimension)
+    int64_t pos = 0;
+    std::vector<double> host_out;
+    double* out_dev = out;
+    if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
+
+    auto n_for_tau = [&](int tau) { int64_t n = 0; for (int r = 0; r < n_runs; r++) { int64_t T = h->run_off[r + 1] - h->run_off[r]; if (T > tau) n += T - tau; } return n; };
+
+    while (pos < n_jobs) {
+        const int L = jobs[pos].n_cond;
+        if (L < 0 || L > SCRIBE_MAX_COND) fail(SCRIBE_E_ARG, "n_cond out of range");
+        const int dz = L + 1, D = dz + 2;
+        // chunk: same n_cond, bounded workspace
+        std::unordered_map<ColKey, int, ColKeyHash> colmap;
+        std::vector<ColSpec> specs;
+        std::vector<JobDesc> hj;
+        std::vector<int> colidx;          // D per job
+        int n_max = 0;
+        int64_t end = pos;
+        size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0);
+        while (end < n_jobs && jobs[end].n_cond == L && (end - pos) < 262144) {
+            const scribe_job& jb = jobs[end];
+            if (jb.src < 0 || jb.src >= h->n_genes || jb.dst < 0 || jb.dst >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
+            if (jb.delay < 1) fail(SCRIBE_E_ARG, "delay must be >= 1");
+            int tau = jb.delay;
+            for (int c = 0; c < L; c++) {
+                if (jb.cond_gene[c] < 0 || jb.cond_gene[c] >= h->n_genes) fail(SCRIBE_E_ARG, "conditioning gene out of range");
+                if (jb.cond_delay[c] < 1) fail(SCRIBE_E_ARG, "conditioning delay must be >= 1");
+                tau = std::max(tau, jb.cond_delay[c]);
+            }
+            const int64_t n = n_for_tau(tau);
+            if (n < 1) fail(SCRIBE_E_LENGTH, "delay leaves no samples");
+            if (n > 2000000) fail(SCRIBE_E_ARG, "too many cells");
+            const int64_t new_nmax = std::max<int64_t>(n_max, n);
+            // workspace estimate if this job is added
+            const size_t ws = (size_t)(specs.size() + D) * new_nmax * 8 + (size_t)(end - pos + 1) * new_nmax * per_point;
+            if (end > pos && ws > h->ws_budget) break;
+            n_max = (int)new_nmax;
+            const double sx = scales ? scales[3 * end] : 1.0, sy = scales ? scales[3 * end + 1] : 1.0, sz = scales ? scales[3 * end + 2] : 1.0;
+            auto get = [&](int gene, int shift, int diff, double sc) {
+                ColKey key{gene, shift, tau, diff, 0};
+                std::memcpy(&key.scale_bits, &sc, 8);
+                auto it = colmap.find(key);
+                if (it != colmap.end()) return it->second;
+                const int id = (int)specs.size();
+                specs.push_back(ColSpec{gene, shift, tau, diff, sc});
+                colmap.emplace(key, id);
+                return id;
+            };
+            colidx.push_back(get(jb.src, tau - jb.delay, 0, sx));                    // x   (cn:147,:266)
+            colidx.push_back(get(jb.dst, tau, differential ? 1 : 0, sy));            // y   (cn:151-153,:269-271)
+            for (int c = L - 1; c >= 0; c--)                                         // z: cond[L-1] .. cond[0], then dst's past (cn:273-278)
+                colidx.push_back(get(jb.cond_gene[c], tau - jb.cond_delay[c], 0, sz));
+            colidx.push_back(get(jb.dst, tau - 1, 0, sz));                           //     (cn:149,:267)
+            JobDesc jd; std::memset(&jd, 0, sizeof(jd)); jd.n = (int)n;
+            hj.push_back(jd);
+            h->st.point_pairs += n * n;
+            end++;
+        }
+        const int64_t nj = end - pos;
+        const int64_t stride = n_max;
+        h->cols.ensure(sizeof(double) * specs.size() * stride);
+        h->specs.ensure(sizeof(ColSpec) * specs.size());
+        CU(cudaMemcpyAsync(h->specs.p, specs.data(), sizeof(ColSpec) * specs.size(), cudaMemcpyHostToDevice, h->stream));
+        h->st.h2d_bytes += sizeof(ColSpec) * specs.size();
+        {
+            dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 64), (unsigned)specs.size());
+            // gridDim.y limit is 65535
+            for (size_t c0 = 0; c0 < specs.size(); c0 += 65535) {
+                grid.y = (unsigned)std::min<size_t>(65535, specs.size() - c0);
+                gather_lagged_kernel<<<grid, TPB, 0, h->stream>>>(h->E.as<double>(), h->n_cells, h->run_off_d.as<int64_t>(), n_runs,
+                    h->specs.as<ColSpec>() + c0, h->cols.as<double>() + c0 * stride, stride);
+                CU(cudaGetLastError());
+                h->st.kernel_launches++;
+            }
+        }
+        for (int64_t j = 0; j < nj; j++)
+            for (int c = 0; c < D; c++) hj[j].col[c] = h->cols.as<double>() + (size_t)colidx[j * D + c] * stride;
+        run_jobs(h, hj, n_max, 1, 1, dz, o, out_dev + pos, false, nullptr, nullptr);
+        pos = end;
+    }
+    if (!out_is_device && n_jobs > 0) {
+        CU(cudaMemcpyAsync(out, out_dev, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, h->stream));
+        h->st.d2h_bytes += sizeof(double) * n_jobs;
+    }
+    end_call(h);
+}
+
+void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, int drop_zero,
+                   const scribe_opts* o, double* out, bool out_is_device, int32_t* n_eff)
+{
+    check_opts(o);
+    if (o->estimator != SCRIBE_EST_CMI) fail(SCRIBE_E_ARG, "dynamics coupling uses cmi");
+    if (h->cg == 0) fail(SCRIBE_E_STATE, "no coupling matrices uploaded");
+    if (n_jobs < 0 || (n_jobs > 0 && (!src || !dst || !out))) fail(SCRIBE_E_ARG, "NULL jobs/out");
+    for (int64_t j = 0; j < n_jobs; j++)
+        if (src[j] < 0 || src[j] >= h->cg || dst[j] < 0 || dst[j] >= h->cg) fail(SCRIBE_E_ARG, "gene index out of range");
+    begin_call(h);
+    const int64_t N = h->cc;
+    double* out_dev = out;
+    if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (3 * N * 8))));
+    h->idx32a.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
+    h->idx32b.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
+    h->neff.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
+    CU(cudaMemcpyAsync(h->idx32a.p, src, sizeof(int32_t) * n_jobs, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->idx32b.p, dst, sizeof(int32_t) * n_jobs, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += 2 * sizeof(int32_t) * n_jobs;
+    std::vector<int32_t> neff_host(n_jobs);
+    for (int64_t pos = 0; pos < n_jobs; pos += chunk) {
+        const int64_t nj = std::min(chunk, n_jobs - pos);
+        h->cols.ensure(sizeof(double) * 3 * N * nj);
+        std::vector<JobDesc> hj(nj);
+        for (int64_t j = 0; j < nj; j++) {
+            std::memset(&hj[j], 0, sizeof(JobDesc));
+            double* b = h->cols.as<double>() + (size_t)j * 3 * N;
+            hj[j].col[0] = b; hj[j].col[1] = b + N; hj[j].col[2] = b + 2 * N;
+            hj[j].n = (int)N; hj[j].qoff = j * N;
+        }
+        h->jobs.ensure(sizeof(JobDesc) * nj);
+        CU(cudaMemcpyAsync(h->jobs.p, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
+        h->st.h2d_bytes += sizeof(JobDesc) * nj;
+        coupling_prep_kernel<<<(unsigned)nj, TPB, 0, h->stream>>>(h->S.as<double>(), h->Y.as<double>(), N,
+            h->idx32a.as<int32_t>() + pos, h->idx32b.as<int32_t>() + pos, drop_zero, h->cols.as<double>(), N,
+            h->jobs.as<JobDesc>(), h->neff.as<int32_t>() + pos);
+        CU(cudaGetLastError());
+        h->st.kernel_launches++;
+        CU(cudaMemcpyAsync(neff_host.data() + pos, h->neff.as<int32_t>() + pos, sizeof(int32_t) * nj, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->st.d2h_bytes += sizeof(int32_t) * nj;
+        for (int64_t j = 0; j < nj; j++) h->st.point_pairs += (int64_t)neff_host[pos + j] * neff_host[pos + j];
+        run_jobs(h, hj, (int)N, 1, 1, 1, o, out_dev + pos, true, nullptr, nullptr);
+    }
+    if (n_eff) std::memcpy(n_eff, neff_host.data(), sizeof(int32_t) * n_jobs);
+    if (!out_is_device && n_jobs > 0) {
+        CU(cudaMemcpyAsync(out, out_dev, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, h->stream));
+        h->st.d2h_bytes += sizeof(double) * n_jobs;
+    }
+    end_call(h);
+}
+
+template <class F> int guarded(scribe_handle* h, F&& f) {
+    if (!h) { g_err = "NULL handle"; return SCRIBE_E_ARG; }
+    try { Guard g(h); f(); g_err.clear(); return SCRIBE_OK; }
+    catch (const Fail& e) { g_err = e.msg; cudaGetLastError(); return e.code; }
+    catch (const std::exception& e) { g_err = e.what(); return SCRIBE_E_ARG; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int scribe_create(int device, scribe_handle** out) {
+    if (!out) { g_err = "NULL out"; return SCRIBE_E_ARG; }
+    *out = nullptr;
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            fail(SCRIBE_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); scribe_b200 has no CPU fallback");
+        if (device < 0) CU(cudaGetDevice(&device));
+        if (device >= count) fail(SCRIBE_E_ARG, "device index out of range");
+        scribe_handle* h = new scribe_handle();
+        h->device = device;
+        int prev = 0; cudaGetDevice(&prev);
+        CU(cudaSetDevice(device));
+        cudaDeviceProp p;
+        CU(cudaGetDeviceProperties(&p, device));
+        h->sm_count = p.multiProcessorCount;
+        cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+        h->mem_bytes = p.totalGlobalMem;
+        std::snprintf(h->name, sizeof(h->name), "%s", p.name);
+        if (p.major < 10) { delete h; cudaSetDevice(prev); fail(SCRIBE_E_CUDA, "scribe_b200 is built for sm_100a only"); }
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&h->ev_call0)); CU(cudaEventCreate(&h->ev_call1));
+        CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
+        h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
+        cudaSetDevice(prev);
+        *out = h;
+        g_err.clear();
+        return SCRIBE_OK;
+    } catch (const Fail& e) { g_err = e.msg; return e.code; }
+}
+
+void scribe_destroy(scribe_handle* h) {
+    if (!h) return;
+    Guard g(h);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
+                      &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single})
+        b->release();
+    cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int scribe_device_info(scribe_handle* h, int32_t* sm_count, int32_t* clock_khz, int64_t* mem_bytes, char* name, int32_t name_len) {
+    if (!h) { g_err = "NULL handle"; return SCRIBE_E_ARG; }
+    if (sm_count) *sm_count = h->sm_count;
+    if (clock_khz) *clock_khz = h->clock_khz;
+    if (mem_bytes) *mem_bytes = (int64_t)h->mem_bytes;
+    if (name && name_len > 0) std::snprintf(name, name_len, "%s", h->name);
+    return SCRIBE_OK;
+}
+
+int scribe_get_stats(scribe_handle* h, scribe_stats* out) {
+    if (!h || !out) { g_err = "NULL argument"; return SCRIBE_E_ARG; }
+    *out = h->st;
+    return SCRIBE_OK;
+}
+
+int scribe_estimate(scribe_handle* h, const double* x, const double* y, const double* z, int64_t n,
+                    int32_t dx, int32_t dy, int32_t dz, const scribe_opts* opts, double* out) {
+    return guarded(h, [&] { single_job(h, x, y, z, n, dx, dy, dz, opts, out, nullptr); });
+}
+
+int scribe_debug_counts(scribe_handle* h, const double* x, const double* y, const double* z, int64_t n,
+                        int32_t dx, int32_t dy, int32_t dz, const scribe_opts* opts,
+                        double* eps, int32_t* counts, double* wsum, double* weights) {
+    return guarded(h, [&] {
+        DebugPtrs d; d.eps = eps; d.cnt = counts; d.wsum = wsum; d.weights = weights;
+        double v;
+        try { single_job(h, x, y, z, n, dx, dy, dz, opts, &v, &d); }
+        catch (const Fail& e) { if (e.code != SCRIBE_E_DOMAIN) throw; }   // counts were still produced
+    });
+}
+
+int scribe_upload_matrix(scribe_handle* h, const double* E, int64_t n_genes, int64_t n_cells,
+                         const int64_t* run_offsets, int32_t n_runs) {
+    return guarded(h, [&] {
+        if (!E || n_genes < 1 || n_cells < 1) fail(SCRIBE_E_ARG, "empty expression matrix");
+        std::vector<int64_t> ro;
+        if (run_offsets && n_runs > 0) ro.assign(run_offsets, run_offsets + n_runs + 1);
+        else ro = {0, n_cells};
+        if (ro.front() != 0 || ro.back() != n_cells) fail(SCRIBE_E_ARG, "run_offsets must span [0, n_cells]");
+        for (size_t r = 1; r < ro.size(); r++) if (ro[r] < ro[r - 1]) fail(SCRIBE_E_ARG, "run_offsets must be non-decreasing");
+        begin_call(h);
+        h->E.ensure(sizeof(double) * n_genes * n_cells);
+        CU(cudaMemcpyAsync(h->E.p, E, sizeof(double) * n_genes * n_cells, cudaMemcpyHostToDevice, h->stream));
+        h->run_off_d.ensure(sizeof(int64_t) * ro.size());
+        CU(cudaMemcpyAsync(h->run_off_d.p, ro.data(), sizeof(int64_t) * ro.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->st.h2d_bytes = sizeof(double) * n_genes * n_cells + sizeof(int64_t) * ro.size();
+        h->n_genes = n_genes; h->n_cells = n_cells; h->run_off = ro;
+        end_call(h);
+    });
+}
+
+int scribe_lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
+                       int32_t differential, const double* scales, double* out_host) {
+    return guarded(h, [&] { lagged_jobs(h, jobs, n_jobs, opts, differential, scales, out_host, false); });
+}
+int scribe_lagged_jobs_dev(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
+                           int32_t differential, const double* scales, double* out_dev) {
+    return guarded(h, [&] { lagged_jobs(h, jobs, n_jobs, opts, differential, scales, out_dev, true); });
+}
+
+int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, int64_t n_genes, int64_t n_cells) {
+    return guarded(h, [&] {
+        if (!S || !Y || n_genes < 1 || n_cells < 1) fail(SCRIBE_E_ARG, "empty coupling matrices");
+        if (n_cells > 2000000) fail(SCRIBE_E_ARG, "too many cells");
+        begin_call(h);
+        const size_t bytes = sizeof(double) * n_genes * n_cells;
+        h->S.ensure(bytes); h->Y.ensure(bytes);
+        CU(cudaMemcpyAsync(h->S.p, S, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->Y.p, Y, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->st.h2d_bytes = 2 * bytes;
+        h->cg = n_genes; h->cc = n_cells;
+        end_call(h);
+    });
+}
+
+int scribe_coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, int32_t drop_zero_cells,
+                         const scribe_opts* opts, double* out_host, int32_t* n_eff) {
+    return guarded(h, [&] { coupling_jobs(h, src, dst, n_jobs, drop_zero_cells, opts, out_host, false, n_eff); });
+}
+int scribe_coupling_jobs_dev(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, int32_t drop_zero_cells,
+                             const scribe_opts* opts, double* out_dev, int32_t* n_eff) {
+    return guarded(h, [&] { coupling_jobs(h, src, dst, n_jobs, drop_zero_cells, opts, out_dev, true, n_eff); });
+}
+
+}  // extern "C"

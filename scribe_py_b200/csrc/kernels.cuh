@@ -1,0 +1,550 @@
+// kernels.cuh -- sm_100a device code of the KSG hot path.
+//
+// Everything here computes in FP64 on purpose.  The reference (scipy cKDTree, float64) decides ball
+// membership with `max_c |a_c - b_c| <= eps_i` where eps_i is itself such a difference, so neighbour
+// counts are only reproducible bit-for-bit if the differences and comparisons are done in float64.
+// B200 (unlike B300) keeps a real FP64 pipe: measured 64 lanes/clk/SM for DADD/DSETP
+// (tools/microbench.cu -> profiles/microbench_r1.jsonl), i.e. half the FP32 FADD rate, which makes the
+// exact path only ~1.4x slower than an (inexact) FP32 one -- see DESIGN.md "Why FP64".
+//
+// Layout: a "job" is one estimator evaluation on N points of joint dimension D = dx+dy+dz.  Its columns
+// live dimension-major in HBM (D pointers to N contiguous doubles, JobDesc).  A CTA owns a block of
+// TPB*Q query points held in registers and streams all N candidates through shared memory in tiles;
+// every lane reads the same candidate (LDS broadcast), so the inner loops are pure FP64-pipe work:
+//   pass 1 (kNN)   : 3 DADD + 3 chained DSETP per point pair, register top-(k+1) insert off the hot path
+//   pass 2 (count) : D DADD + (dz+3) chained DSETP + 4 predicated integer adds per point pair
+// followed by the digamma terms and a deterministic block reduction (one partial per CTA).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace scribe {
+
+constexpr int TPB  = 256;     // threads per CTA (all kernels)
+constexpr int TILE = 512;     // candidates staged per shared-memory tile
+constexpr int MAXD = 16;      // == SCRIBE_MAX_DIM
+constexpr int GEN_KCAP = 64;  // generic kernel: k+1 <= 64
+
+struct JobDesc {
+    const double* col[MAXD];  // x dims, then y dims, then z dims
+    const double* w;          // uniformisation weights (cumi/umi) or nullptr
+    int64_t qoff;             // offset of this job's per-point outputs (eps/counts/...) in the workspace
+    int32_t n;                // points
+    int32_t pad;
+};
+
+struct PointOut {             // optional per-point outputs (debug entry point, generic path, kNN-only mode)
+    double*  eps;             // [qoff + i]
+    int32_t* cnt;             // [4*(qoff+i) + s]
+    double*  wsum;            // [2*(qoff+i) + s]
+};
+
+enum : int { MODE_CMI = 0, MODE_MI = 1, MODE_KNN_ONLY = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// digamma for real argument, double precision (replaces scipy.special.digamma at
+// information_estimators.py:102-107,:169-172,:264,:399-402).  |error| ~1e-15, far inside the 1e-5 budget.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline double digamma_pos(double x) {   // x > 0, finite
+    double acc = 0.0;
+    while (x < 10.0) { acc -= 1.0 / x; x += 1.0; }
+    const double xi = 1.0 / x, x2 = xi * xi;
+    const double ser = x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240 - x2 * (1.0 / 132
+                       - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+    return acc + log(x) - 0.5 * xi - ser;
+}
+
+__host__ __device__ inline double digamma_f64(double x) {
+    if (x != x) return x;
+    if (x == 0.0) return copysign(INFINITY, -x);          // scipy: digamma(0.0) = -inf, digamma(-0.0) = +inf
+    if (isinf(x)) return x > 0 ? x : NAN;
+    if (x < 0.0) {                                        // reflection: psi(x) = psi(1-x) - pi/tan(pi x)
+        const double r = x - floor(x);
+        if (r == 0.0) return NAN;
+        return digamma_pos(1.0 - x) - 3.14159265358979323846 / tan(3.14159265358979323846 * r);
+    }
+    return digamma_pos(x);
+}
+
+__device__ __forceinline__ double psi_int(const double* __restrict__ tab, int n) { return __ldg(tab + n); }
+
+// Deterministic block sum: fixed shuffle tree inside a warp, fixed order across warps.
+__device__ __forceinline__ double block_sum(double v, double* smem8) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem8[wid] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+        #pragma unroll
+        for (int w = 0; w < TPB / 32; w++) s += smem8[w];
+    }
+    return s;   // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused dense kernel (Chebyshev metric): mi / cmi / cumi and kNN-only.
+//   replaces tree_xyz.query(...)[0][k] + 3-4 query_ball_point per point + digamma + mean
+//   (information_estimators.py:101-109, :165-173, :396-403)
+// ------------------------------------------------------------------------------------------------
+template <int KCAP>
+__device__ __forceinline__ void topk_insert(double (&L)[KCAP], double d) {
+    // L ascending; caller guarantees d < L[KCAP-1]
+    L[KCAP - 1] = d;
+    #pragma unroll
+    for (int t = KCAP - 1; t > 0; --t) {
+        const double a = L[t - 1], b = L[t];
+        const bool s = b < a;
+        L[t - 1] = s ? b : a;
+        L[t]     = s ? a : b;
+    }
+}
+
+template <int DX, int DY, int DZ, int KCAP, int Q, bool WEIGHTED>
+__global__ void __launch_bounds__(TPB)
+ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, int mode,
+                 const double* __restrict__ psi_tab, double* __restrict__ partial, PointOut po)
+{
+    constexpr int D = DX + DY + DZ;
+    __shared__ double tile[D][TILE];
+    __shared__ double wtile[WEIGHTED ? TILE : 1];
+    __shared__ double red[TPB / 32];
+
+    const int job = blockIdx.x / blocks_per_job;
+    const int qb  = blockIdx.x - job * blocks_per_job;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int q0 = qb * (TPB * Q);
+    if (q0 >= n) return;                                   // uniform: this CTA has no query points
+    const int tid = threadIdx.x;
+
+    double qc[Q][D];
+    int    qi[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = q0 + q * TPB + tid;
+        qi[q] = i;
+        const int ii = i < n ? i : n - 1;                  // idle slots shadow the last point (results dropped)
+        #pragma unroll
+        for (int c = 0; c < D; c++) qc[q][c] = jd.col[c][ii];
+    }
+
+    // ---------------- pass 1: k-th neighbour distance in the joint space ----------------
+    // L holds the KCAP smallest values seen; the lowest KCAP-(k+1) slots are pre-filled with -inf sentinels
+    // so that L[KCAP-1] is always the (k+1)-th smallest joint distance (self included) = eps_i.
+    double L[Q][KCAP];
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
+
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int base = 0; base < n; base += TILE) {
+        const int cnt = min(TILE, n - base);
+        __syncthreads();
+        for (int t = tid; t < TILE; t += TPB) {
+            #pragma unroll
+            for (int c = 0; c < D; c++) tile[c][t] = (t < cnt) ? jd.col[c][base + t] : qnan;   // NaN never compares true
+        }
+        __syncthreads();
+        const int cnt4 = (cnt + 3) & ~3;
+        #pragma unroll 4
+        for (int j = 0; j < cnt4; j++) {
+            double cc[D];
+            #pragma unroll
+            for (int c = 0; c < D; c++) cc[c] = tile[c][j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                double ad[D];
+                bool lt = true;
+                #pragma unroll
+                for (int c = 0; c < D; c++) { ad[c] = fabs(qc[q][c] - cc[c]); lt = lt & (ad[c] < L[q][KCAP - 1]); }
+                if (lt) {
+                    double d = ad[0];
+                    #pragma unroll
+                    for (int c = 1; c < D; c++) d = fmax(d, ad[c]);
+                    topk_insert<KCAP>(L[q], d);
+                }
+            }
+        }
+    }
+
+    double eps[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) eps[q] = L[q][KCAP - 1];   // +inf when n <= k, like cKDTree's padding
+
+    if (mode == MODE_KNN_ONLY) {
+        #pragma unroll
+        for (int q = 0; q < Q; q++) if (qi[q] < n) po.eps[jd.qoff + qi[q]] = eps[q];
+        return;
+    }
+
+    // ---------------- pass 2: closed-ball counts in the marginal subspaces ----------------
+    int nxyz[Q], nxz[Q], nyz[Q], nz[Q];
+    double wyz[Q], wz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
+
+    for (int base = 0; base < n; base += TILE) {
+        const int cnt = min(TILE, n - base);
+        __syncthreads();
+        for (int t = tid; t < TILE; t += TPB) {
+            #pragma unroll
+            for (int c = 0; c < D; c++) tile[c][t] = (t < cnt) ? jd.col[c][base + t] : qnan;
+            if (WEIGHTED) wtile[t] = (t < cnt) ? jd.w[base + t] : 0.0;
+        }
+        __syncthreads();
+        const int cnt4 = (cnt + 3) & ~3;
+        #pragma unroll 4
+        for (int j = 0; j < cnt4; j++) {
+            double cc[D];
+            #pragma unroll
+            for (int c = 0; c < D; c++) cc[c] = tile[c][j];
+            double wj = 0.0;
+            if (WEIGHTED) wj = wtile[j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                bool pz = true, px = true, py = true;
+                #pragma unroll
+                for (int c = 0; c < DZ; c++) pz = pz & (fabs(qc[q][DX + DY + c] - cc[DX + DY + c]) <= eps[q]);
+                #pragma unroll
+                for (int c = 0; c < DX; c++) px = px & (fabs(qc[q][c] - cc[c]) <= eps[q]);
+                #pragma unroll
+                for (int c = 0; c < DY; c++) py = py & (fabs(qc[q][DX + c] - cc[DX + c]) <= eps[q]);
+                if (DZ == 0) pz = !(cc[0] != cc[0]);       // mi: every real candidate is in the (empty-z) ball; padding is not
+                const bool pxz = px & pz, pyz = py & pz, pxyz = pxz & py;
+                nz[q]   += pz   ? 1 : 0;
+                nxz[q]  += pxz  ? 1 : 0;
+                nyz[q]  += pyz  ? 1 : 0;
+                nxyz[q] += pxyz ? 1 : 0;
+                if (WEIGHTED) { wz[q] += pz ? wj : 0.0; wyz[q] += pyz ? wj : 0.0; }
+            }
+        }
+    }
+
+    // ---------------- digamma terms + reduction ----------------
+    double acc = 0.0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = qi[q];
+        if (i < n) {
+            const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;   // self removed
+            double term;
+            if (WEIGHTED) {
+                const double wi = jd.w[i];
+                const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
+                // information_estimators.py:399-402
+                term = wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
+                if (po.wsum) { po.wsum[2 * (jd.qoff + i)] = Wyz; po.wsum[2 * (jd.qoff + i) + 1] = Wz; }
+            } else if (mode == MODE_MI) {
+                // information_estimators.py:102-107 (here x -> "xz" slot, y -> "yz" slot)
+                term = psi_int(psi_tab, n) + psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c);
+            } else {
+                // information_estimators.py:169-172
+                term = psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            }
+            acc += term;
+            if (po.eps) po.eps[jd.qoff + i] = eps[q];
+            if (po.cnt) { int32_t* o = po.cnt + 4 * (jd.qoff + i); o[0] = a; o[1] = b; o[2] = c; o[3] = d; }
+        }
+    }
+    const double s = block_sum(acc, red);
+    if (tid == 0) partial[blockIdx.x] = s;
+}
+
+// out[job] = (sum of that job's CTA partials, in CTA order) / n      (np.mean at :109,:173,:403)
+__global__ void finalize_mean_kernel(const JobDesc* __restrict__ jobs, const double* __restrict__ partial,
+                                     int blocks_per_job, int n_jobs, double* __restrict__ out)
+{
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= n_jobs) return;
+    const int n = jobs[job].n;
+    double s = 0.0;
+    for (int b = 0; b < blocks_per_job; b++) s += partial[(size_t)job * blocks_per_job + b];
+    out[job] = (n > 0) ? s / (double)n : NAN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernel: any dx,dy,dz (D <= 16), k+1 <= 64, Chebyshev or Euclidean, optional weights.
+// One thread per query point, candidates read through L1/L2 (all lanes hit the same address).
+// Writes eps / counts / weighted sums per point; a finish kernel turns them into the estimate.
+//   euclid: scipy's p=2 convention -- d2 = sum diff^2 (no FMA contraction), r = sqrt(d2_k), ball test
+//   sum_{c in S} diff^2 <= r*r  (information_estimators.py:263,:268,:272-273)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+ksg_generic_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int dx, int dy, int dz, int k,
+                   int euclid, int knn_only, PointOut po)
+{
+    const int job = blockIdx.x / blocks_per_job;
+    const int qb  = blockIdx.x - job * blocks_per_job;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int i = qb * TPB + threadIdx.x;
+    if (i >= n) return;
+    const int D = dx + dy + dz;
+    double qc[MAXD];
+    for (int c = 0; c < D; c++) qc[c] = jd.col[c][i];
+
+    double L[GEN_KCAP];
+    const int kc = k + 1;
+    for (int t = 0; t < kc; t++) L[t] = INFINITY;
+    for (int j = 0; j < n; j++) {
+        double d = 0.0;
+        for (int c = 0; c < D; c++) {
+            const double df = qc[c] - jd.col[c][j];
+            d = euclid ? __dadd_rn(d, __dmul_rn(df, df)) : fmax(d, fabs(df));
+        }
+        if (d < L[kc - 1]) {
+            int t = kc - 1;
+            while (t > 0 && L[t - 1] > d) { L[t] = L[t - 1]; --t; }
+            L[t] = d;
+        }
+    }
+    double eps = L[k];
+    double thr = eps;
+    if (euclid) { eps = __dsqrt_rn(eps); thr = __dmul_rn(eps, eps); }
+    po.eps[jd.qoff + i] = eps;
+    if (knn_only) return;
+
+    int nxyz = 0, nxz = 0, nyz = 0, nz = 0;
+    double wyz = 0.0, wz = 0.0, wy = 0.0;
+    const bool weighted = jd.w != nullptr;
+    for (int j = 0; j < n; j++) {
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int c = 0; c < dx; c++) { const double df = qc[c] - jd.col[c][j]; ax = euclid ? __dadd_rn(ax, __dmul_rn(df, df)) : fmax(ax, fabs(df)); }
+        for (int c = dx; c < dx + dy; c++) { const double df = qc[c] - jd.col[c][j]; ay = euclid ? __dadd_rn(ay, __dmul_rn(df, df)) : fmax(ay, fabs(df)); }
+        for (int c = dx + dy; c < D; c++) { const double df = qc[c] - jd.col[c][j]; az = euclid ? __dadd_rn(az, __dmul_rn(df, df)) : fmax(az, fabs(df)); }
+        const bool px = ax <= thr, py = ay <= thr, pz = az <= thr;      // dz == 0 -> az = 0 -> pz true
+        const bool pxz = px & pz, pyz = py & pz, pxyz = pxz & py;
+        nz += pz; nxz += pxz; nyz += pyz; nxyz += pxyz;
+        if (weighted) { const double wj = jd.w[j]; wz += pz ? wj : 0.0; wyz += pyz ? wj : 0.0; wy += py ? wj : 0.0; }
+    }
+    int32_t* o = po.cnt + 4 * (jd.qoff + i);
+    o[0] = nxyz - 1; o[1] = nxz - 1; o[2] = nyz - 1; o[3] = nz - 1;
+    if (po.wsum && weighted) {
+        const double wi = jd.w[i];
+        po.wsum[2 * (jd.qoff + i)]     = (euclid ? wy : wyz) - wi;      // umi: W_y - w_i ; cumi: W_yz - w_i
+        po.wsum[2 * (jd.qoff + i) + 1] = wz - wi;
+    }
+}
+
+// Finish kernel for the generic path: one CTA per job, deterministic strided accumulation + block sum.
+//   est 0 mi, 1 cmi, 2 umi (sum of w_i (log n_x + log W_y); flag set on log(<=0)), 3 cumi
+__global__ void __launch_bounds__(TPB)
+ksg_finish_kernel(const JobDesc* __restrict__ jobs, int est, const double* __restrict__ psi_tab,
+                  PointOut po, double* __restrict__ out, int* __restrict__ domain_flag)
+{
+    __shared__ double red[TPB / 32];
+    const JobDesc& jd = jobs[blockIdx.x];
+    const int n = jd.n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += TPB) {
+        const int32_t* c = po.cnt + 4 * (jd.qoff + i);
+        double term;
+        if (est == 0)      term = psi_int(psi_tab, n) + psi_int(psi_tab, c[0]) - psi_int(psi_tab, c[1]) - psi_int(psi_tab, c[2]);
+        else if (est == 1) term = psi_int(psi_tab, c[0]) - psi_int(psi_tab, c[1]) - psi_int(psi_tab, c[2]) + psi_int(psi_tab, c[3]);
+        else if (est == 3) {
+            const double wi = jd.w[i];
+            term = wi * psi_int(psi_tab, c[0]) + wi * -psi_int(psi_tab, c[1]) + wi * -digamma_f64(po.wsum[2 * (jd.qoff + i)])
+                 + wi * digamma_f64(po.wsum[2 * (jd.qoff + i) + 1]);
+        } else {
+            const double wi = jd.w[i];
+            const int nx = c[1];
+            const double Wy = po.wsum[2 * (jd.qoff + i)];
+            // math.log raises ValueError for arguments <= 0 (and for NaN? no: log(nan)=nan) -- information_estimators.py:274,:276
+            if (nx <= 0 || Wy <= 0.0) *domain_flag = 1;
+            term = wi * log((double)nx) + wi * log(Wy);
+        }
+        acc += term;
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = (est == 2) ? s : ((n > 0) ? s / (double)n : NAN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian KDE inverse densities (replaces KernelDensity(bandwidth=bw).fit(P).score_samples(P),
+// information_estimators.py:248-251, :385-388).  u_i = 1 / sum_j exp(-|P_i-P_j|^2 / (2 bw^2));
+// the normalising constant and 1/N cancel in w = u / mean(u).  Differences and squares in FP64
+// (the exponent argument needs ~1e-9 absolute accuracy in d^2 at bw=0.01), 2^x on the MUFU in FP32.
+// Coordinates are pre-scaled by sqrt(log2(e)/(2 bw^2)) so the argument is just -(sum of squares).
+// ------------------------------------------------------------------------------------------------
+template <int DP, int Q>
+__global__ void __launch_bounds__(TPB)
+kde_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, const int* __restrict__ dims, double scale,
+           double* __restrict__ u_out)
+{
+    __shared__ double tile[DP][TILE];
+    const int job = blockIdx.x / blocks_per_job;
+    const int qb  = blockIdx.x - job * blocks_per_job;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int q0 = qb * (TPB * Q);
+    if (q0 >= n) return;
+    const int tid = threadIdx.x;
+    const double* cp[DP];
+    #pragma unroll
+    for (int c = 0; c < DP; c++) cp[c] = jd.col[dims[c]];
+
+    double qc[Q][DP];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = q0 + q * TPB + tid;
+        const int ii = i < n ? i : n - 1;
+        #pragma unroll
+        for (int c = 0; c < DP; c++) qc[q][c] = cp[c][ii] * scale;
+    }
+    double S[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) S[q] = 0.0;
+
+    for (int base = 0; base < n; base += TILE) {
+        const int cnt = min(TILE, n - base);
+        __syncthreads();
+        for (int t = tid; t < TILE; t += TPB) {
+            #pragma unroll
+            for (int c = 0; c < DP; c++) tile[c][t] = (t < cnt) ? cp[c][base + t] * scale : INFINITY;   // exp2(-inf) = 0
+        }
+        __syncthreads();
+        float s32[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) s32[q] = 0.f;
+        const int cnt4 = (cnt + 3) & ~3;
+        #pragma unroll 4
+        for (int j = 0; j < cnt4; j++) {
+            double cc[DP];
+            #pragma unroll
+            for (int c = 0; c < DP; c++) cc[c] = tile[c][j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                double d2 = 0.0;
+                #pragma unroll
+                for (int c = 0; c < DP; c++) { const double df = qc[q][c] - cc[c]; d2 = fma(df, df, d2); }
+                float e;
+                const float a = -(float)d2;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+                s32[q] += e;
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) S[q] += (double)s32[q];
+    }
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = q0 + q * TPB + tid;
+        if (i < n) u_out[jd.qoff + i] = 1.0 / S[q];
+    }
+}
+
+// kNN-density inverse densities: u_i = 1/dens_i, dens_i = k_density / N / r_i^dim
+// (information_estimators.py:255-256, :391-392).  r_i == 0 -> dens = inf -> u = 0, as in numpy.
+__global__ void knn_density_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k_density, int dim,
+                                   const double* __restrict__ r, double* __restrict__ u_out)
+{
+    const int job = blockIdx.x / blocks_per_job;
+    const int qb  = blockIdx.x - job * blocks_per_job;
+    const JobDesc& jd = jobs[job];
+    const int i = qb * TPB + threadIdx.x;
+    if (i >= jd.n) return;
+    const double dens = (double)k_density / (double)jd.n / pow(r[jd.qoff + i], (double)dim);
+    u_out[jd.qoff + i] = 1.0 / dens;
+}
+
+// w = u / mean(u), in place; one CTA per job, deterministic.
+__global__ void __launch_bounds__(TPB)
+normalize_weights_kernel(const JobDesc* __restrict__ jobs, double* __restrict__ u)
+{
+    __shared__ double red[TPB / 32];
+    __shared__ double mean_s;
+    const JobDesc& jd = jobs[blockIdx.x];
+    const int n = jd.n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += TPB) acc += u[jd.qoff + i];
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) mean_s = s / (double)n;
+    __syncthreads();
+    const double m = mean_s;
+    for (int i = threadIdx.x; i < n; i += TPB) u[jd.qoff + i] = u[jd.qoff + i] / m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lagged-embedding materialisation (replaces the per-pair list comprehensions at
+// causal_network.py:147-153,:167-173,:266-277).  One output column = (gene, shift, tau, diff, scale):
+//   for run r, t in [0, T_r - tau):  v = E[gene][run_off[r] + t + shift]   (diff: E[p-1] - E[p])
+// ------------------------------------------------------------------------------------------------
+struct ColSpec { int32_t gene, shift, tau, diff; double scale; };
+
+__global__ void __launch_bounds__(TPB)
+gather_lagged_kernel(const double* __restrict__ E, int64_t n_cells, const int64_t* __restrict__ run_off, int n_runs,
+                     const ColSpec* __restrict__ specs, double* __restrict__ out, int64_t col_stride)
+{
+    const ColSpec sp = specs[blockIdx.y];
+    const double* row = E + (size_t)sp.gene * n_cells;
+    double* o = out + (size_t)blockIdx.y * col_stride;
+    int64_t lag_base = 0;
+    for (int r = 0; r < n_runs; r++) {
+        const int64_t T = run_off[r + 1] - run_off[r];
+        const int64_t len = T - sp.tau;
+        if (len <= 0) continue;
+        for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < len; t += (int64_t)gridDim.x * TPB) {
+            const int64_t p = run_off[r] + t + sp.shift;
+            double v = sp.diff ? (row[p - 1] - row[p]) : row[p];
+            if (sp.scale != 1.0) v = v / sp.scale;
+            o[lag_base + t] = v;
+        }
+        lag_base += len;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dynamics-coupling prep (replaces Scribe.py:119-133): per job gather x = S[src], y = Y[dst], z = S[dst],
+// keep cells with (x + y) + z > 0 (float64, this association order) and compact them stably.
+// One CTA per job; writes 3 columns of stride `col_stride` and the kept count into jobs[job].n.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y, int64_t n_cells,
+                     const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int drop_zero,
+                     double* __restrict__ cols, int64_t col_stride, JobDesc* __restrict__ jobs, int32_t* __restrict__ n_eff)
+{
+    __shared__ int warp_cnt[TPB / 32];
+    __shared__ int base_s;
+    const int job = blockIdx.x;
+    const double* xs = S + (size_t)src[job] * n_cells;
+    const double* zs = S + (size_t)dst[job] * n_cells;
+    const double* ys = Y + (size_t)dst[job] * n_cells;
+    double* ox = cols + (size_t)job * 3 * col_stride;
+    double* oy = ox + col_stride;
+    double* oz = oy + col_stride;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < n_cells; c0 += TPB) {
+        const int64_t c = c0 + tid;
+        double x = 0, y = 0, z = 0;
+        bool keep = false;
+        if (c < n_cells) {
+            x = xs[c]; y = ys[c]; z = zs[c];
+            keep = drop_zero ? (__dadd_rn(__dadd_rn(x, y), z) > 0.0) : true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; w++) off += warp_cnt[w];
+        if (keep) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            ox[pos] = x; oy[pos] = y; oz[pos] = z;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < TPB / 32; w++) t += warp_cnt[w]; base_s += t; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        jobs[job].n = base_s;
+        if (n_eff) n_eff[job] = base_s;
+    }
+}
+
+}  // namespace scribe

@@ -1,0 +1,211 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the reference-generated fixtures and the oracle.
+Bars: neighbour counts and eps bit-exact; mi/cmi values <= 1e-9 (budget 1e-5); umi/cumi <= 1e-6 (budget 1e-5:
+the KDE exponent is evaluated by the FP32 MUFU); top-100 edge ranking identical."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import recipes
+from oracle import ksg_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL_EXACT = 1e-9     # estimators whose per-point inputs are integers (counts): only summation order differs
+TOL_KDE = 1e-6       # uniformised estimators
+SETS = {"a": recipes.gv_a, "b": recipes.gv_b, "poisson": recipes.gv_poisson, "d5": recipes.gv_d5, "dims": recipes.gv_dims}
+
+
+@pytest.fixture(scope="module")
+def S():
+    import scribe_py_b200 as s
+    s._lib.default_handle()          # raises if the CUDA library / device is missing
+    return s
+
+
+def close(got, ref, tol):
+    if np.isnan(ref):
+        return np.isnan(got)
+    return abs(got - ref) <= tol
+
+
+@pytest.mark.parametrize("path", ["auto", "generic"])
+@pytest.mark.parametrize("name", list(SETS))
+def test_counts_bit_exact(S, golden, name, path):
+    x, y, z = SETS[name]()
+    d = S.information_estimators.ksg_debug("cmi", x, y, z, path=path)
+    assert np.array_equal(d["eps"], golden[f"{name}_eps"])
+    assert np.array_equal(d["counts"], golden[f"{name}_cnt"])
+    d = S.information_estimators.ksg_debug("mi", x, y, path=path)
+    assert np.array_equal(d["eps"], golden[f"{name}_mi_eps"])
+    assert np.array_equal(d["counts"][:3], golden[f"{name}_mi_cnt"])
+
+
+@pytest.mark.parametrize("name", list(SETS))
+def test_estimator_values(S, golden, name):
+    x, y, z = SETS[name]()
+    L = lambda a: a.tolist()
+    assert close(S.cmi(L(x), L(y), L(z)), float(golden[f"{name}_cmi"]), TOL_EXACT)
+    assert close(S.cmi(x, y, z, normalization=True), float(golden[f"{name}_cmi_norm"]), TOL_EXACT)
+    assert close(S.cmi(x, y, z, k=3), float(golden[f"{name}_cmi_k3"]), TOL_EXACT)
+    assert close(S.cmi(x, y, z, k=10), float(golden[f"{name}_cmi_k10"]), TOL_EXACT)
+    assert close(S.mi(L(x), L(y)), float(golden[f"{name}_mi"]), TOL_EXACT)
+    assert close(S.mi(x, y, k=3), float(golden[f"{name}_mi_k3"]), TOL_EXACT)
+
+
+@pytest.mark.parametrize("name", list(SETS))
+def test_uniformised_values(S, golden, name):
+    x, y, z = SETS[name]()
+    assert close(S.cumi(x, y, z), float(golden[f"{name}_cumi_kde"]), TOL_KDE)
+    assert close(S.cumi(x, y, z, bw=0.05, k=4), float(golden[f"{name}_cumi_kde_bw"]), TOL_KDE)
+    assert close(S.cumi(x, y, z, density_estimation_method="knn"), float(golden[f"{name}_cumi_knn"]), TOL_KDE)
+    assert close(S.umi(x, y), float(golden[f"{name}_umi_kde"]), TOL_KDE)
+    ref = float(golden[f"{name}_umi_knn"])
+    if np.isinf(ref):
+        with pytest.raises(ValueError):
+            S.umi(x, y, density_estimation_method="knn")
+    else:
+        assert close(S.umi(x, y, density_estimation_method="knn"), ref, TOL_KDE)
+
+
+def test_uniformised_per_point(S):
+    """weights and weighted ball sums against the oracle's float64 brute force."""
+    x, y, z = recipes.gv_a()
+    d = S.information_estimators.ksg_debug("cumi", x, y, z)
+    P = np.concatenate((x, y, z), axis=1)
+    w = o.kde_weights(P[:, [0, 2]], 0.01)
+    eps, cnt, W = o.knn_counts(P, [(0, 1, 2), (0, 2), (1, 2), (2,)], 5, weights=w)
+    assert np.array_equal(d["eps"], eps) and np.array_equal(d["counts"], cnt)
+    assert np.allclose(d["weights"], w, rtol=2e-6, atol=0)
+    assert np.allclose(d["wsum"][0], W[2], rtol=2e-6) and np.allclose(d["wsum"][1], W[3], rtol=2e-6)
+
+
+@pytest.mark.parametrize("n", [4, 6, 7, 12, 40])
+def test_tiny_inputs(S, golden, n):
+    x, y, z = recipes.gv_small(n)
+    assert close(S.cmi(x, y, z), float(golden[f"small{n}_cmi"]), TOL_EXACT)
+    assert close(S.mi(x, y), float(golden[f"small{n}_mi"]), TOL_EXACT)
+
+
+def test_error_behaviour(S):
+    x, y, z = recipes.gv_small(12)
+    with pytest.raises(AssertionError, match="Lists should have same length"):
+        S.cmi(x, y[:-1], z)
+    with pytest.raises(AssertionError, match="Lists should have same length"):
+        S.mi(x[:-1], y)
+    with pytest.raises(AssertionError, match="Set k smaller"):
+        S.umi(x, y, k=12)
+    with pytest.raises(ValueError, match="not recognized"):
+        S.cumi(x, y, z, density_estimation_method="histogram")
+    with pytest.raises(ValueError, match="not recognized"):
+        S.umi(x, y, density_estimation_method="histogram")
+    assert S.vd(3) == pytest.approx(o.vd(3), abs=0)
+
+
+def test_random_sizes_against_oracle(S):
+    """ragged sizes around the tile / CTA boundaries, continuous and tied data"""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 255, 256, 257, 511, 512, 513, 1025, 1537):
+        x = rng.standard_normal((n, 1)); z = np.round(rng.standard_normal((n, 1)), 1); y = x + z + rng.standard_normal((n, 1))
+        d = S.information_estimators.ksg_debug("cmi", x, y, z)
+        eps, cnt = o.cmi_debug(x, y, z)
+        assert np.array_equal(d["eps"], eps), n
+        assert np.array_equal(d["counts"], cnt), n
+        got, ref = S.cmi(x, y, z), o.cmi(x, y, z)
+        assert close(got, ref, TOL_EXACT) or (np.isinf(ref) and got == ref), n
+
+
+def test_dynamics_coupling_c1(S, golden):
+    spl, vel, genes = recipes.gv_c()
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, genes)
+    assert S.causal_net_dynamics_coupling(ad) is None
+    M = ad.uns["causal_net"]["RDI"]
+    assert list(M.index) == genes and list(M.columns) == genes
+    got = M.to_numpy(dtype=float)
+    assert np.abs(got - golden["c_matrix"]).max() <= TOL_EXACT
+    flat = lambda A: np.argsort(-A, axis=None, kind="stable")[:100]
+    assert np.array_equal(flat(got), flat(golden["c_matrix"]))          # top-100 edge ranking identical
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, genes)
+    out = S.causal_net_dynamics_coupling(ad, TFs=genes[:5], Targets=genes[3:9], drop_zero_cells=False, normalize=False,
+                                         copy=True)
+    assert out is ad
+    assert np.abs(ad.uns["causal_net"]["RDI"].to_numpy(dtype=float) - golden["c_matrix_nodrop"]).max() <= TOL_EXACT
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "unspliced": np.abs(vel) * 3}, genes)
+    S.causal_net_dynamics_coupling(ad, TFs=genes[:4], Targets=genes[:6], t1_key="unspliced")
+    assert np.abs(ad.uns["causal_net"]["RDI"].to_numpy(dtype=float) - golden["c_matrix_t1"]).max() <= TOL_EXACT
+    with pytest.raises(Exception):
+        S.causal_net_dynamics_coupling(ad, TFs=["nope"])
+
+
+def _model_single(S, X, genes):
+    df = pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID"))
+    return S.causal_model(df)
+
+
+def test_rdi_single_run(S, golden):
+    X, genes, delays = recipes.gv_d()
+    for tag, kw, tol in (("", {}, TOL_EXACT), ("_u", {"uniformization": True}, TOL_KDE),
+                         ("_diff", {"differential_mode": True}, TOL_EXACT)):
+        m = _model_single(S, X, genes)
+        r = m.rdi(delays, **kw)
+        assert set(r.keys()) == set(delays) | {"MAX"}
+        for d in delays:
+            got = r[d].to_numpy(dtype=float)
+            assert np.allclose(got, golden[f"d_rdi{tag}_{d}"], atol=tol, rtol=0, equal_nan=True), (tag, d)
+            assert np.isnan(np.diag(got)).all()
+        assert np.allclose(r["MAX"].to_numpy(dtype=float), golden[f"d_rdi{tag}_MAX"], atol=tol, rtol=0)
+        assert list(r[delays[0]].index) == genes
+
+
+def test_rdi_crdi_multi_run(S, golden):
+    runs, genes, delays = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    r = m.rdi(delays)
+    for d in delays:
+        assert np.allclose(r[d].to_numpy(dtype=float), golden[f"e_rdi_{d}"], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    assert np.allclose(r["MAX"].to_numpy(dtype=float), golden["e_rdi_MAX"], atol=TOL_EXACT, rtol=0)
+    assert np.allclose(m.crdi(L=1).to_numpy(dtype=float), golden["e_crdi_L1"], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    assert np.allclose(m.crdi(L=2).to_numpy(dtype=float), golden["e_crdi_L2"], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    m.rdi([1, 2], uniformization=True)
+    assert np.allclose(m.crdi(L=1, uniformization=True).to_numpy(dtype=float), golden["e_crdi_L1_u"], atol=TOL_KDE,
+                       rtol=0, equal_nan=True)
+
+
+def test_crdi_runs_rdi_when_missing(S):
+    runs, genes, _ = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    with pytest.warns(UserWarning, match="RUNNING RDI NOW"):
+        c = m.crdi(L=1)
+    assert 1 in m.rdi_results and c.shape == (6, 6)
+
+
+def test_c2_slice(S, golden):
+    E = recipes.rdi_synthetic(8, 400, 2)
+    m = _model_single(S, E, ["g%d" % i for i in range(8)])
+    r = m.rdi([1, 5, 10])
+    for d in (1, 5, 10):
+        assert np.allclose(r[d].to_numpy(dtype=float), golden[f"c2_rdi_{d}"], atol=TOL_EXACT, rtol=0, equal_nan=True)
+
+
+def test_full_size_properties(S):
+    """C2-sized job (N = 2000): size-independent checks that need no CPU oracle at full scale --
+    n_xyz >= k with equality off ties, ball nesting n_xyz <= n_xz, n_yz <= n_z <= N-1, permutation invariance,
+    and agreement of the fused and the generic kernels."""
+    E = recipes.rdi_synthetic(3, 2000, 9)
+    x, y, z = E[0, :-1, None], E[1, 1:, None], E[1, :-1, None]
+    d = S.information_estimators.ksg_debug("cmi", x, y, z)
+    c = d["counts"]
+    assert (c[0] >= 5).all() and (c[0] == 5).mean() > 0.99
+    assert (c[0] <= c[1]).all() and (c[0] <= c[2]).all() and (c[1] <= c[3]).all() and (c[2] <= c[3]).all()
+    assert (c[3] <= len(x) - 1).all()
+    g = S.information_estimators.ksg_debug("cmi", x, y, z, path="generic")
+    assert np.array_equal(g["eps"], d["eps"]) and np.array_equal(g["counts"], c)
+    perm = np.random.default_rng(0).permutation(len(x))
+    v0, v1 = S.cmi(x, y, z), S.cmi(x[perm], y[perm], z[perm])
+    assert abs(v0 - v1) < 1e-12
+    # sampled rows against the oracle's definition
+    P = np.concatenate((x, y, z), axis=1)
+    for i in (0, 1, 777, 1998):
+        dist = np.abs(P - P[i]).max(axis=1)
+        assert d["eps"][i] == np.sort(dist)[5]
+        assert c[3][i] == (np.abs(P[:, 2] - P[i, 2]) <= d["eps"][i]).sum() - 1
