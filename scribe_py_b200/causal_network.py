@@ -164,20 +164,12 @@ class causal_model(object):
     def _frame(self, M, node_ids):
         return pd.DataFrame(M, index=node_ids, columns=node_ids)
 
-    # ------------------------------------------------------------------ RDI
-    def rdi(self, delays, number_of_processes=1, uniformization=False, differential_mode=False):
-        """Pairwise Restricted Directed Information for every delay in `delays` (causal_network.py:112-187).
-
-        Returns (and stores in self.rdi_results) {delay: G x G DataFrame (rows = source, columns = target,
-        NaN diagonal)} plus "MAX", the element-wise maximum over delays (-inf diagonal).
-        `number_of_processes` is accepted and ignored: parallelism comes from the GPU(s)."""
+    def _rdi_plan(self, delays, differential_mode=False):
+        """Host-side job table of one rdi() call: every ordered pair x delay, ordered delay-major, then
+        target, then source, so that a rank's contiguous slab shares its targets' y/z columns."""
         delays = list(delays)
         node_ids, E, run_off = self._dense()
         G = len(node_ids)
-        h = _lib.default_handle()
-        h.upload_matrix(E, run_off)
-
-        # job order: delay-major, then target, then source (a rank's slab shares target columns)
         tgt, src = np.meshgrid(np.arange(G, dtype=np.int32), np.arange(G, dtype=np.int32), indexing="ij")
         off = tgt != src
         tgt, src = tgt[off], src[off]
@@ -194,12 +186,33 @@ class causal_model(object):
                 sl = slice(i * per, (i + 1) * per)
                 sx, sy, sz = st[d]
                 scales[sl, 0] = sx[src]; scales[sl, 1] = sy[tgt]; scales[sl, 2] = sz[tgt]
+        return {"delays": delays, "node_ids": node_ids, "E": E, "run_off": run_off, "jobs": jobs, "scales": scales,
+                "src": src, "tgt": tgt, "per": per}
+
+    @staticmethod
+    def _rdi_execute(plan, uniformization=False, differential_mode=False):
+        """Evaluate a plan against the matrix resident on this rank's GPU; all ranks get all results."""
+        h = _lib.default_handle()
+        jobs, scales = plan["jobs"], plan["scales"]
         opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
 
         def evaluate(lo, hi):
             return h.lagged_jobs(jobs[lo:hi], opts, differential_mode, None if scales is None else scales[lo:hi])
 
-        vals = _dist.sharded_evaluate(len(jobs), evaluate)
+        return _dist.sharded_evaluate(len(jobs), evaluate)
+
+    # ------------------------------------------------------------------ RDI
+    def rdi(self, delays, number_of_processes=1, uniformization=False, differential_mode=False):
+        """Pairwise Restricted Directed Information for every delay in `delays` (causal_network.py:112-187).
+
+        Returns (and stores in self.rdi_results) {delay: G x G DataFrame (rows = source, columns = target,
+        NaN diagonal)} plus "MAX", the element-wise maximum over delays (-inf diagonal).
+        `number_of_processes` is accepted and ignored: parallelism comes from the GPU(s)."""
+        plan = self._rdi_plan(delays, differential_mode)
+        _lib.default_handle().upload_matrix(plan["E"], plan["run_off"])
+        vals = self._rdi_execute(plan, uniformization, differential_mode)
+        delays, node_ids, src, tgt, per = plan["delays"], plan["node_ids"], plan["src"], plan["tgt"], plan["per"]
+        G = len(node_ids)
         self.rdi_results = {}
         for i, d in enumerate(delays):
             M = np.full((G, G), np.nan)

@@ -98,7 +98,7 @@ def test_error_behaviour(S):
         S.cumi(x, y, z, density_estimation_method="histogram")
     with pytest.raises(ValueError, match="not recognized"):
         S.umi(x, y, density_estimation_method="histogram")
-    assert S.vd(3) == pytest.approx(o.vd(3), abs=0)
+    assert S.vd(3) == pytest.approx(o.vd(3), abs=1e-15)
 
 
 def test_random_sizes_against_oracle(S):
