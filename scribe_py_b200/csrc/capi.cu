@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -55,6 +56,7 @@ struct scribe_handle {
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
+    int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
 };
 
 namespace {
@@ -91,12 +93,22 @@ void check_opts(const scribe_opts* o) {
 }
 
 // ---- fused-kernel dispatch -------------------------------------------------------------------------
-using FusedFn = void (*)(const JobDesc*, int, int, int, const double*, double*, PointOut);
+using FusedFn = void (*)(const JobDesc*, int, int, int, int, const double*, double*, PointOut);
+
+template <int DX, int DY, int DZ, int KCAP, bool W>
+FusedFn pick_q(int q) {
+    switch (q) {
+        case 1: return ksg_fused_kernel<DX, DY, DZ, KCAP, 1, W>;
+        case 2: return ksg_fused_kernel<DX, DY, DZ, KCAP, 2, W>;
+        case 4: return ksg_fused_kernel<DX, DY, DZ, KCAP, 4, W>;
+    }
+    return nullptr;
+}
 
 template <int DX, int DY, int DZ, bool W>
 FusedFn pick_kq(int kcap, int q) {
-    if (kcap == 6)  return q == 1 ? ksg_fused_kernel<DX, DY, DZ, 6, 1, W>  : ksg_fused_kernel<DX, DY, DZ, 6, 2, W>;
-    if (kcap == 16) return q == 1 ? ksg_fused_kernel<DX, DY, DZ, 16, 1, W> : ksg_fused_kernel<DX, DY, DZ, 16, 2, W>;
+    if (kcap == 6)  return pick_q<DX, DY, DZ, 6, W>(q);
+    if (kcap == 16) return pick_q<DX, DY, DZ, 16, W>(q == 4 ? 2 : q);
     return nullptr;
 }
 
@@ -152,9 +164,11 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
 
     const int k = o->k;
     const int kcap = (k + 1 <= 6) ? 6 : ((k + 1 <= 16) ? 16 : 0);
-    const int q = (n_max > 2 * TPB) ? 2 : 1;
+    int q = (n_max > 2 * TPB) ? 2 : 1;
+    if (h->force_q) q = h->force_q;
     FusedFn fused = nullptr;
     if (o->path == SCRIBE_PATH_AUTO && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
+    if (kcap == 16 && q == 4) q = 2;
     const bool need_points = (fused == nullptr) || dbg != nullptr;
 
     for (int64_t j = 0; j < nj; j++) hj[j].qoff = j * (int64_t)n_max;
@@ -234,7 +248,10 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         h->partial.ensure(sizeof(double) * nj * bpj_f);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * bpj_f, h->stream));
         const int mode = (est == SCRIBE_EST_MI) ? MODE_MI : MODE_CMI;
-        fused<<<(unsigned)(nj * bpj_f), TPB, 0, h->stream>>>(dj, bpj_f, k, mode, h->psi.as<double>(), h->partial.as<double>(), po);
+        const int cap = std::min((n_max + 3) & ~3, FUSED_TILE_MAX);
+        const size_t smem = sizeof(double) * (size_t)cap * (D + (weighted ? 1 : 0));
+        if (smem > 40 * 1024) CU(cudaFuncSetAttribute((const void*)fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused<<<(unsigned)(nj * bpj_f), TPB, smem, h->stream>>>(dj, bpj_f, k, mode, cap, h->psi.as<double>(), h->partial.as<double>(), po);
         CU(cudaGetLastError());
         finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), bpj_f, (int)nj, out_dev);
         CU(cudaGetLastError());
@@ -523,6 +540,7 @@ int scribe_create(int device, scribe_handle** out) {
         CU(cudaEventCreate(&h->ev_call0)); CU(cudaEventCreate(&h->ev_call1));
         CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
         h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
+        if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) h->force_q = v; }
         cudaSetDevice(prev);
         *out = h;
         g_err.clear();

@@ -103,14 +103,27 @@ __device__ __forceinline__ void topk_insert(double (&L)[KCAP], double d) {
     }
 }
 
+// predicated accumulators: one issue slot each (the compiler otherwise emits add + select pairs)
+__device__ __forceinline__ void inc_if(int& n, bool p) {
+    asm("{.reg .pred q; setp.ne.b32 q, %1, 0; @q add.s32 %0, %0, 1;}" : "+r"(n) : "r"((int)p));
+}
+__device__ __forceinline__ void add_if(double& acc, double v, bool p) {
+    asm("{.reg .pred q; setp.ne.b32 q, %2, 0; @q add.f64 %0, %0, %1;}" : "+d"(acc) : "d"(v), "r"((int)p));
+}
+
+// Shared-memory tile of candidates: D rows of `cap` doubles (+ one row of weights), dynamic size.
+// cap = min(round_up(n_max, 4), FUSED_TILE_MAX): jobs up to FUSED_TILE_MAX points are staged ONCE for both passes.
+constexpr int FUSED_TILE_MAX = 2048;
+
 template <int DX, int DY, int DZ, int KCAP, int Q, bool WEIGHTED>
 __global__ void __launch_bounds__(TPB)
-ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, int mode,
+ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, int mode, int cap,
                  const double* __restrict__ psi_tab, double* __restrict__ partial, PointOut po)
 {
     constexpr int D = DX + DY + DZ;
-    __shared__ double tile[D][TILE];
-    __shared__ double wtile[WEIGHTED ? TILE : 1];
+    extern __shared__ double smem[];
+    double* tile  = smem;                 // [D][cap]
+    double* wtile = smem + D * cap;       // [cap] (WEIGHTED only)
     __shared__ double red[TPB / 32];
 
     const int job = blockIdx.x / blocks_per_job;
@@ -125,12 +138,35 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
     int    qi[Q];
     #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const int i = q0 + q * TPB + tid;
+        const int i = q0 + tid * Q + q;                    // a warp owns 32*Q CONSECUTIVE points (see j0 below)
         qi[q] = i;
         const int ii = i < n ? i : n - 1;                  // idle slots shadow the last point (results dropped)
         #pragma unroll
         for (int c = 0; c < D; c++) qc[q][c] = jd.col[c][ii];
     }
+
+    const int ntiles = (n + cap - 1) / cap;
+    // Candidates are visited starting AT this warp's own query points (first the tile that holds them, and inside
+    // it from the warp's first point, wrapping round): for pseudotime-ordered (autocorrelated) cells the temporal
+    // neighbours are close in the joint space too, so the k-th-distance threshold tightens within the first few
+    // dozen candidates and the top-k insert path is rarely taken afterwards.  Any order gives the same result.
+    const int tile0 = min(q0 / cap, ntiles - 1);
+    const int wq0 = q0 + (tid & ~31) * Q;                  // this warp's first query point
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    auto load_tile = [&](int t) {
+        const int base = t * cap;
+        const int cnt = min(cap, n - base);
+        const int cnt4 = (cnt + 3) & ~3;
+        __syncthreads();
+        for (int i = tid; i < cnt4; i += TPB) {
+            #pragma unroll
+            for (int c = 0; c < D; c++) tile[c * cap + i] = (i < cnt) ? jd.col[c][base + i] : qnan;   // NaN never compares true
+            if (WEIGHTED) wtile[i] = (i < cnt) ? jd.w[base + i] : 0.0;
+        }
+        __syncthreads();
+        return cnt4;
+    };
 
     // ---------------- pass 1: k-th neighbour distance in the joint space ----------------
     // L holds the KCAP smallest values seen; the lowest KCAP-(k+1) slots are pre-filled with -inf sentinels
@@ -141,32 +177,39 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
         #pragma unroll
         for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
 
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int base = 0; base < n; base += TILE) {
-        const int cnt = min(TILE, n - base);
-        __syncthreads();
-        for (int t = tid; t < TILE; t += TPB) {
+    int cnt4 = 0;
+    for (int tt = 0; tt < ntiles; tt++) {
+        int t = tile0 + tt; if (t >= ntiles) t -= ntiles;
+        cnt4 = load_tile(t);
+        int j = 0;
+        if (tt == 0) { j = (wq0 - t * cap) & ~3; if (j < 0 || j >= cnt4) j = 0; }
+        #pragma unroll 2
+        for (int it = 0; it < cnt4; it += 2, j += 2) {
+            if (j >= cnt4) j = 0;                           // wrap (cnt4 and the start are multiples of 4)
+            double ad[2][Q][D];
+            bool lt[2][Q];
+            bool any = false;
             #pragma unroll
-            for (int c = 0; c < D; c++) tile[c][t] = (t < cnt) ? jd.col[c][base + t] : qnan;   // NaN never compares true
-        }
-        __syncthreads();
-        const int cnt4 = (cnt + 3) & ~3;
-        #pragma unroll 4
-        for (int j = 0; j < cnt4; j++) {
-            double cc[D];
-            #pragma unroll
-            for (int c = 0; c < D; c++) cc[c] = tile[c][j];
-            #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                double ad[D];
-                bool lt = true;
+            for (int jj = 0; jj < 2; jj++) {
                 #pragma unroll
-                for (int c = 0; c < D; c++) { ad[c] = fabs(qc[q][c] - cc[c]); lt = lt & (ad[c] < L[q][KCAP - 1]); }
-                if (lt) {
-                    double d = ad[0];
+                for (int q = 0; q < Q; q++) {
+                    bool l = true;
                     #pragma unroll
-                    for (int c = 1; c < D; c++) d = fmax(d, ad[c]);
-                    topk_insert<KCAP>(L[q], d);
+                    for (int c = 0; c < D; c++) { ad[jj][q][c] = fabs(qc[q][c] - tile[c * cap + j + jj]); l = l & (ad[jj][q][c] < L[q][KCAP - 1]); }
+                    lt[jj][q] = l;
+                    any = any | l;
+                }
+            }
+            if (any) {                                      // rare once the threshold has settled
+                #pragma unroll
+                for (int jj = 0; jj < 2; jj++) {
+                    #pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        double d = ad[jj][q][0];
+                        #pragma unroll
+                        for (int c = 1; c < D; c++) d = fmax(d, ad[jj][q][c]);
+                        if (lt[jj][q] && d < L[q][KCAP - 1]) topk_insert<KCAP>(L[q], d);   // re-check: the first insert moves the bar
+                    }
                 }
             }
         }
@@ -188,21 +231,13 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
     #pragma unroll
     for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
 
-    for (int base = 0; base < n; base += TILE) {
-        const int cnt = min(TILE, n - base);
-        __syncthreads();
-        for (int t = tid; t < TILE; t += TPB) {
-            #pragma unroll
-            for (int c = 0; c < D; c++) tile[c][t] = (t < cnt) ? jd.col[c][base + t] : qnan;
-            if (WEIGHTED) wtile[t] = (t < cnt) ? jd.w[base + t] : 0.0;
-        }
-        __syncthreads();
-        const int cnt4 = (cnt + 3) & ~3;
+    for (int tt = 0; tt < ntiles; tt++) {
+        if (ntiles > 1) cnt4 = load_tile(tt);              // a single tile is still resident from pass 1
         #pragma unroll 4
         for (int j = 0; j < cnt4; j++) {
             double cc[D];
             #pragma unroll
-            for (int c = 0; c < D; c++) cc[c] = tile[c][j];
+            for (int c = 0; c < D; c++) cc[c] = tile[c * cap + j];
             double wj = 0.0;
             if (WEIGHTED) wj = wtile[j];
             #pragma unroll
@@ -216,11 +251,8 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
                 for (int c = 0; c < DY; c++) py = py & (fabs(qc[q][DX + c] - cc[DX + c]) <= eps[q]);
                 if (DZ == 0) pz = !(cc[0] != cc[0]);       // mi: every real candidate is in the (empty-z) ball; padding is not
                 const bool pxz = px & pz, pyz = py & pz, pxyz = pxz & py;
-                nz[q]   += pz   ? 1 : 0;
-                nxz[q]  += pxz  ? 1 : 0;
-                nyz[q]  += pyz  ? 1 : 0;
-                nxyz[q] += pxyz ? 1 : 0;
-                if (WEIGHTED) { wz[q] += pz ? wj : 0.0; wyz[q] += pyz ? wj : 0.0; }
+                inc_if(nz[q], pz); inc_if(nxz[q], pxz); inc_if(nyz[q], pyz); inc_if(nxyz[q], pxyz);
+                if (WEIGHTED) { add_if(wz[q], wj, pz); add_if(wyz[q], wj, pyz); }
             }
         }
     }

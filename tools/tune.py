@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Kernel timing sweep: python tools/tune.py  (env SCRIBE_B200_Q=1|2|4 overrides queries per thread)."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import recipes
+import scribe_py_b200 as S
+from scribe_py_b200 import _lib
+
+def run(G, T, delays, est, reps=2):
+    E = recipes.rdi_synthetic(G, T, 2) if T <= 4000 else np.random.default_rng(0).standard_normal((G, T)).cumsum(axis=1) * 0.05 + np.random.default_rng(1).standard_normal((G, T))
+    h = _lib.default_handle()
+    h.upload_matrix(E)
+    src, dst = np.nonzero(~np.eye(G, dtype=bool))
+    jobs = np.zeros(len(src) * len(delays), dtype=_lib.JOB_DTYPE)
+    for i, d in enumerate(delays):
+        sl = slice(i * len(src), (i + 1) * len(src))
+        jobs["src"][sl] = src; jobs["dst"][sl] = dst; jobs["delay"][sl] = d
+    opts = _lib.make_opts(est, 5)
+    best = None
+    for _ in range(reps + 1):
+        v = h.lagged_jobs(jobs, opts)
+        st = h.stats()
+        if best is None or st["estimator_ms"] < best["estimator_ms"]:
+            best = st
+    pairs = best["point_pairs"]
+    clk = 1.965e9
+    cps = best["estimator_ms"] * 1e-3 * clk * 148 * 4 / (pairs / 32)        # SMSP-cycles per warp-step (32 point pairs)
+    print("Q=%s est=%d G=%d T=%d jobs=%d  est_ms=%.2f total_ms=%.2f  evals/s=%.0f  pairs/s=%.3e  clk/warp-step=%.2f  checksum=%.12f"
+          % (os.environ.get("SCRIBE_B200_Q", "auto"), est, G, T, len(jobs), best["estimator_ms"], best["total_ms"],
+             len(jobs) / (best["total_ms"] * 1e-3), pairs / (best["estimator_ms"] * 1e-3), cps, float(np.nansum(v))), flush=True)
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "cmi"
+    if what == "cmi":
+        run(60, 2000, [1, 5, 10], _lib.EST_CMI)
+        run(24, 20000, [1], _lib.EST_CMI)
+    elif what == "cumi":
+        run(40, 2000, [1, 5, 10], _lib.EST_CUMI)
+        run(16, 20000, [1], _lib.EST_CUMI)
