@@ -1,0 +1,135 @@
+"""CPU tests of the host side of the drop-in: with the device replaced by tests/fake_device.FakeHandle (which
+evaluates jobs with the oracle) the Python drivers must reproduce the reference-generated fixtures -- this
+checks job construction, lag conventions, frames, MAX / argmax, top-incoming selection, cRDI conditioning sets
+and the dynamics-coupling preprocessing.  Plus the sharding arithmetic and a world_size-2 gloo all-gather."""
+import os
+import socket
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import recipes
+from fake_device import FakeHandle
+
+
+@pytest.fixture()
+def S(monkeypatch):
+    import scribe_py_b200 as s
+    fake = FakeHandle()
+    monkeypatch.setattr(s._lib, "default_handle", lambda device=None: fake)
+    s._fake = fake
+    return s
+
+
+def test_rdi_single_run_host_logic(S, golden):
+    X, genes, delays = recipes.gv_d()
+    for tag, kw in (("", {}), ("_diff", {"differential_mode": True})):
+        m = S.causal_model(pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID")))
+        r = m.rdi(delays, **kw)
+        for d in delays:
+            assert np.allclose(r[d].to_numpy(dtype=float), golden[f"d_rdi{tag}_{d}"], atol=1e-12, rtol=0, equal_nan=True)
+        assert np.allclose(r["MAX"].to_numpy(dtype=float), golden[f"d_rdi{tag}_MAX"], atol=1e-12, rtol=0)
+        assert np.isneginf(np.diag(r["MAX"].to_numpy(dtype=float))).all()
+
+
+def test_rdi_crdi_multi_run_host_logic(S, golden):
+    runs, genes, delays = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    r = m.rdi(delays)
+    for d in delays:
+        assert np.allclose(r[d].to_numpy(dtype=float), golden[f"e_rdi_{d}"], atol=1e-12, rtol=0, equal_nan=True)
+    assert np.allclose(m.crdi(L=1).to_numpy(dtype=float), golden["e_crdi_L1"], atol=1e-12, rtol=0, equal_nan=True)
+    assert np.allclose(m.crdi(L=2).to_numpy(dtype=float), golden["e_crdi_L2"], atol=1e-12, rtol=0, equal_nan=True)
+
+
+def test_nan_padding_and_ragged_runs(S):
+    runs, genes, _ = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    ids, E, ro = m._dense()
+    assert list(ro) == [0, 150, 260] and E.shape == (6, 260) and not np.isnan(E).any()
+    assert np.array_equal(E[2, 150:], runs[1][2])
+    bad = recipes.multi_run_frame(runs, genes)
+    bad.iloc[3, 5] = np.nan                      # one gene loses a cell -> lengths differ -> the reference's assertion
+    with pytest.raises(AssertionError, match="same length"):
+        S.causal_model(bad)._dense()
+
+
+def test_dynamics_coupling_host_logic(S, golden):
+    spl, vel, genes = recipes.gv_c()
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, genes)
+    S.causal_net_dynamics_coupling(ad, TFs=genes[:3], Targets=genes[:4])
+    M = ad.uns["causal_net"]["RDI"]
+    assert M.shape == (3, 4)
+    assert np.allclose(M.to_numpy(dtype=float), golden["c_matrix"][:3, :4], atol=1e-12, rtol=0)
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "unspliced": np.abs(vel) * 3}, genes)
+    S.causal_net_dynamics_coupling(ad, TFs=genes[:4], Targets=genes[:6], t1_key="unspliced")
+    assert np.allclose(ad.uns["causal_net"]["RDI"].to_numpy(dtype=float), golden["c_matrix_t1"], atol=1e-12, rtol=0)
+    from scipy import sparse
+    ad = recipes.FakeAnnData({"spliced": sparse.csr_matrix(spl), "velocity": vel.copy()}, genes)
+    S.causal_net_dynamics_coupling(ad, TFs=genes[:2], Targets=genes[:3])
+    assert np.allclose(ad.uns["causal_net"]["RDI"].to_numpy(dtype=float), golden["c_matrix"][:2, :3], atol=1e-12, rtol=0)
+
+
+def test_clr_matches_definition(S):
+    rng = np.random.default_rng(0)
+    A = pd.DataFrame(rng.random((5, 5)), index=list("abcde"), columns=list("abcde"))
+    out = S.CLR(A)
+    m = A.values
+    zr = (np.round(m, 10) - m.mean(axis=1)) / m.std(axis=1, ddof=1); zr[zr < 0] = 0
+    assert np.allclose(out.values, np.sqrt(zr ** 2))
+    assert list(out.index) == list("abcde")
+
+
+def test_slab_partition():
+    from scribe_py_b200.distributed import slab
+    for n in (0, 1, 7, 8, 29700, 249500):
+        for ws in (1, 2, 3, 4, 8):
+            parts = [slab(n, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scribe_py_b200 as s
+    from scribe_py_b200.distributed import sharded_evaluate
+    seen = []
+
+    def evaluate(lo, hi):
+        seen.append((lo, hi))
+        return np.arange(lo, hi, dtype=np.float64) ** 2 + 0.5
+
+    out = sharded_evaluate(101, evaluate)
+    ok = bool(np.array_equal(out, np.arange(101, dtype=np.float64) ** 2 + 0.5)) and len(seen) == 1
+    # the full rdi() driver, sharded: every rank must end up with the complete matrices
+    fake = FakeHandle()
+    s._lib.default_handle = lambda device=None: fake
+    X, genes, delays = recipes.gv_d()
+    r = s.causal_model(pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID"))).rdi(delays)
+    q.put((rank, ok, seen, fake.calls, r[1].to_numpy(dtype=float), r[2].to_numpy(dtype=float)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding(golden):
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0)); port = s_.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][2] == [(0, 51)] and res[1][2] == [(51, 101)]
+    for rank, ok, seen, calls, r1, r2 in res:
+        assert ok
+        assert calls == [12]                              # 24 jobs (12 ordered pairs x 2 delays) split evenly
+        assert np.allclose(r1, golden["d_rdi_1"], atol=1e-12, rtol=0, equal_nan=True)
+        assert np.allclose(r2, golden["d_rdi_2"], atol=1e-12, rtol=0, equal_nan=True)
