@@ -49,8 +49,11 @@ extern "C" {
 #define SCRIBE_DENSITY_KNN 1
 
 /* kernel path selection (testing / debugging) */
-#define SCRIBE_PATH_AUTO    0  /* fused register-top-k kernels when an instantiation exists       */
+#define SCRIBE_PATH_AUTO    0  /* sorted-sweep kernels for cmi/cumi when instantiated and N >= 256,
+                                  else the dense fused kernels, else the generic kernels          */
 #define SCRIBE_PATH_GENERIC 1  /* runtime-dimension kernels (any dx,dy,dz,k within the limits)     */
+#define SCRIBE_PATH_DENSE   2  /* dense fused kernels: every query visits every candidate          */
+#define SCRIBE_PATH_SWEEP   3  /* sorted-sweep kernels regardless of N                             */
 
 typedef struct scribe_handle scribe_handle;
 
@@ -84,6 +87,10 @@ typedef struct scribe_stats {
     int64_t point_pairs;       /* sum over jobs of N^2 (dense point pairs the estimator visited) */
     int64_t jobs;              /* jobs evaluated                                                 */
     int64_t h2d_bytes, d2h_bytes;
+    /* point-pair visits actually made, per pass: N^2 each for the dense kernels, less for the sorted sweep */
+    int64_t visited_knn;       /* pass 1: k-th neighbour search                                   */
+    int64_t visited_count;     /* pass 2: ball counts                                             */
+    int64_t visited_kde;       /* KDE weights (cumi / umi with density = KDE)                     */
 } scribe_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

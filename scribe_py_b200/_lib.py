@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libscribe_b200.so")
 SCRIBE_OK, E_ARG, E_LENGTH, E_CUDA, E_DOMAIN, E_STATE = 0, 1, 2, 3, 4, 5
 EST_MI, EST_CMI, EST_UMI, EST_CUMI = 0, 1, 2, 3
 DENSITY_KDE, DENSITY_KNN = 0, 1
-PATH_AUTO, PATH_GENERIC = 0, 1
+PATH_AUTO, PATH_GENERIC, PATH_DENSE, PATH_SWEEP = 0, 1, 2, 3
 MAX_COND = 4
 
 
@@ -33,7 +33,7 @@ class Opts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("estimator_launches", C.c_int64), ("estimator_ms", C.c_double),
                 ("total_ms", C.c_double), ("point_pairs", C.c_int64), ("jobs", C.c_int64),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("visited_knn", C.c_int64), ("visited_count", C.c_int64), ("visited_kde", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -99,7 +99,17 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_opts(estimator, k=5, density="kde", k_density=5, bw=0.01, path=PATH_AUTO):
+_PATH_NAMES = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "dense": PATH_DENSE, "sweep": PATH_SWEEP}
+
+
+def default_path():
+    """Kernel path used by the drivers: SCRIBE_B200_PATH=auto|dense|sweep|generic (default auto)."""
+    return _PATH_NAMES[os.environ.get("SCRIBE_B200_PATH", "auto").lower()]
+
+
+def make_opts(estimator, k=5, density="kde", k_density=5, bw=0.01, path=None):
+    if path is None:
+        path = default_path()
     m = str(density).lower()
     if m == "kde":
         d = DENSITY_KDE

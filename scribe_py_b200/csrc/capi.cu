@@ -3,6 +3,7 @@
 // entry point fails.
 #include "../../include/scribe_b200.h"
 #include "kernels.cuh"
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -50,10 +51,11 @@ struct scribe_handle {
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // resident inputs
     DevBuf E, run_off_d; int64_t n_genes = 0, n_cells = 0; std::vector<int64_t> run_off;
-    DevBuf S, Y; int64_t cg = 0, cc = 0;
+    DevBuf S, Y; int64_t cg = 0, cc = 0; bool permS_valid = false;
     // workspaces
     DevBuf psi; int psi_n = 0;
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
+    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS;
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
@@ -131,6 +133,73 @@ FusedFn pick_fused(int dx, int dy, int dz, int kcap, int q, bool weighted) {
     return nullptr;
 }
 
+using SweepFn = void (*)(const JobDesc*, int, int, const double*, double*, PointOut, unsigned long long*);
+
+template <int DZ, bool W>
+SweepFn pick_sweep_k(int kcap) {
+    if (kcap == 6)  return ksg_sweep_kernel<1, 1, DZ, 6, 2, W>;
+    if (kcap == 16) return ksg_sweep_kernel<1, 1, DZ, 16, 2, W>;
+    return nullptr;
+}
+SweepFn pick_sweep(int dx, int dy, int dz, int kcap, bool weighted) {
+    if (dx != 1 || dy != 1) return nullptr;
+    switch (dz) {
+        case 1: return weighted ? pick_sweep_k<1, true>(kcap) : pick_sweep_k<1, false>(kcap);
+        case 2: return weighted ? pick_sweep_k<2, true>(kcap) : pick_sweep_k<2, false>(kcap);
+        case 3: return weighted ? pick_sweep_k<3, true>(kcap) : pick_sweep_k<3, false>(kcap);
+    }
+    return nullptr;
+}
+constexpr int SWEEP_Q = 2;
+constexpr int SWEEP_MIN_N = 256;      // below this the dense kernel's single tile is at least as good
+
+using KdeSweepFn = void (*)(const JobDesc*, int, const int*, double, double*, unsigned long long*);
+KdeSweepFn pick_kde_sweep(int dp) {
+    switch (dp) {
+        case 2: return kde_sweep_kernel<2, 2>;
+        case 3: return kde_sweep_kernel<3, 2>;
+        case 4: return kde_sweep_kernel<4, 2>;
+    }
+    return nullptr;
+}
+
+// Will run_jobs take the sorted-sweep kernels for this configuration?  (callers must then provide JobDesc.perm
+// or pre-sorted columns)
+bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
+    if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) return false;
+    const int kcap = (o->k + 1 <= 6) ? 6 : ((o->k + 1 <= 16) ? 16 : 0);
+    if (!kcap || !pick_sweep(dx, dy, dz, kcap, false)) return false;
+    if (o->path == SCRIBE_PATH_SWEEP) return true;
+    return o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N;
+}
+
+// argsort of n_seg key segments laid out [n_seg][stride] (segment s has len[s] valid items): perm_out[s][r] = index
+// of the r-th smallest key of segment s.  One cub::DeviceSegmentedRadixSort over all segments.
+void sort_segments(scribe_handle* h, const double* keys_in, int n_seg, int64_t stride, const std::vector<int>& len,
+                   int32_t* perm_out)
+{
+    const int64_t total = (int64_t)n_seg * stride;
+    if (total >= (int64_t)1 << 31) fail(SCRIBE_E_ARG, "sort too large for one chunk");
+    h->keys_out.ensure(sizeof(double) * total);
+    h->vals_in.ensure(sizeof(int32_t) * total);
+    std::vector<int> off(2 * (size_t)n_seg);
+    for (int s = 0; s < n_seg; s++) { off[s] = (int)(s * stride); off[n_seg + s] = (int)(s * stride) + len[s]; }
+    h->seg_off.ensure(sizeof(int) * off.size());
+    CU(cudaMemcpyAsync(h->seg_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += sizeof(int) * off.size();
+    iota_segments_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 65535), 256, 0, h->stream>>>(h->vals_in.as<int32_t>(), stride, n_seg);
+    CU(cudaGetLastError());
+    size_t tmp = 0;
+    const int* b = h->seg_off.as<int>(); const int* e = b + n_seg;
+    CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, keys_in, h->keys_out.as<double>(), h->vals_in.as<int32_t>(), perm_out,
+                                                (int)total, n_seg, b, e, 0, 64, h->stream));
+    h->sort_tmp.ensure(tmp + 16);
+    CU(cub::DeviceSegmentedRadixSort::SortPairs(h->sort_tmp.p, tmp, keys_in, h->keys_out.as<double>(), h->vals_in.as<int32_t>(), perm_out,
+                                                (int)total, n_seg, b, e, 0, 64, h->stream));
+    CU(cudaStreamSynchronize(h->stream));         // `off` must outlive the copy; also surfaces sort errors here
+    h->st.kernel_launches += 2;
+}
+
 using KdeFn = void (*)(const JobDesc*, int, const int*, double, double*);
 KdeFn pick_kde(int dp) {
     switch (dp) {
@@ -149,7 +218,8 @@ struct DebugPtrs { double* eps = nullptr; int32_t* cnt = nullptr; double* wsum =
 // Evaluate `hj.size()` jobs whose columns are already in device memory.  out_dev: one double per job.
 // dbg (optional, single-chunk only): host pointers that receive the per-point quantities of job 0..n-1.
 void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int dy, int dz,
-              const scribe_opts* o, double* out_dev, bool n_on_device, const DebugPtrs* dbg, bool* domain_error)
+              const scribe_opts* o, double* out_dev, bool n_on_device, const DebugPtrs* dbg, bool* domain_error,
+              bool have_order = false)
 {
     const int64_t nj = (int64_t)hj.size();
     if (nj == 0) return;
@@ -167,9 +237,18 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     int q = (n_max > 2 * TPB) ? 2 : 1;
     if (h->force_q) q = h->force_q;
     FusedFn fused = nullptr;
-    if (o->path == SCRIBE_PATH_AUTO && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
+    SweepFn sweep = nullptr;
+    if (have_order && want_sweep(o, dx, dy, dz, n_max)) sweep = pick_sweep(dx, dy, dz, kcap, weighted);
+    if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     if (kcap == 16 && q == 4) q = 2;
-    const bool need_points = (fused == nullptr) || dbg != nullptr;
+    const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
+    const int wpj = (n_max + 32 * SWEEP_Q - 1) / (32 * SWEEP_Q);        // warps per job, sweep kernels
+    unsigned long long* visited = nullptr;
+    if (sweep) {
+        h->visited.ensure(3 * sizeof(unsigned long long));
+        CU(cudaMemsetAsync(h->visited.p, 0, 3 * sizeof(unsigned long long), h->stream));
+        visited = h->visited.as<unsigned long long>();
+    }
 
     for (int64_t j = 0; j < nj; j++) hj[j].qoff = j * (int64_t)n_max;
     const int bpj_f = (n_max + TPB * q - 1) / (TPB * q);       // CTAs per job, fused
@@ -209,11 +288,17 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         const int dp = (int)pd.size();
         if (o->density == SCRIBE_DENSITY_KDE) {
             KdeFn kf = pick_kde(dp);
+            KdeSweepFn ks = (sweep && est == SCRIBE_EST_CUMI) ? pick_kde_sweep(dp) : nullptr;
             if (!kf) fail(SCRIBE_E_ARG, "KDE supports at most 6 density dimensions");
             h->dims.ensure(sizeof(int) * MAXD);
             CU(cudaMemcpyAsync(h->dims.p, pd.data(), sizeof(int) * dp, cudaMemcpyHostToDevice, h->stream));
             const double scale = std::sqrt(1.4426950408889634 / (2.0 * o->bw * o->bw));
-            kf<<<(unsigned)(nj * bpj_kde), TPB, 0, h->stream>>>(dj, bpj_kde, h->dims.as<int>(), scale, u);
+            if (ks) {
+                const int bps = (wpj + TPB / 32 - 1) / (TPB / 32);
+                ks<<<(unsigned)(nj * bps), TPB, 0, h->stream>>>(dj, wpj, h->dims.as<int>(), scale, u, visited);
+            } else {
+                kf<<<(unsigned)(nj * bpj_kde), TPB, 0, h->stream>>>(dj, bpj_kde, h->dims.as<int>(), scale, u);
+            }
             CU(cudaGetLastError());
             h->st.kernel_launches++; h->st.estimator_launches++;
         } else {
@@ -244,7 +329,16 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     }
 
     // ---- estimator -----------------------------------------------------------------------------------
-    if (fused) {
+    if (sweep) {
+        h->partial.ensure(sizeof(double) * nj * wpj);
+        CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * wpj, h->stream));
+        const int bps = (wpj + TPB / 32 - 1) / (TPB / 32);
+        sweep<<<(unsigned)(nj * bps), TPB, 0, h->stream>>>(dj, wpj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
+        CU(cudaGetLastError());
+        finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), wpj, (int)nj, out_dev);
+        CU(cudaGetLastError());
+        h->st.kernel_launches += 2; h->st.estimator_launches++;
+    } else if (fused) {
         h->partial.ensure(sizeof(double) * nj * bpj_f);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * bpj_f, h->stream));
         const int mode = (est == SCRIBE_EST_MI) ? MODE_MI : MODE_CMI;
@@ -278,6 +372,18 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     CU(cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1));
     h->st.estimator_ms += ms;
     h->st.jobs += nj;
+    if (sweep) {
+        unsigned long long v[3] = {0, 0, 0};
+        CU(cudaMemcpy(v, h->visited.p, sizeof(v), cudaMemcpyDeviceToHost));
+        h->st.visited_knn += (int64_t)v[0]; h->st.visited_count += (int64_t)v[1]; h->st.visited_kde += (int64_t)v[2];
+        if (weighted && v[2] == 0) for (int64_t j = 0; j < nj; j++) h->st.visited_kde += (int64_t)hj[j].n * hj[j].n;
+    } else if (!n_on_device) {
+        for (int64_t j = 0; j < nj; j++) {
+            const int64_t nn = (int64_t)hj[j].n * hj[j].n;
+            h->st.visited_knn += nn; h->st.visited_count += nn;
+            if (weighted && o->density == SCRIBE_DENSITY_KDE) h->st.visited_kde += nn;
+        }
+    }
 
     if (dbg) {
         const int n = hj[0].n;
@@ -326,7 +432,14 @@ void single_job(scribe_handle* h, const double* x, const double* y, const double
     hj[0].n = (int)n;
     h->out.ensure(sizeof(double));
     bool dom = false;
-    run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom);
+    bool ordered = false;
+    if (want_sweep(o, dx, dy, dz, (int)n)) {                 // argsort of the last conditioning column
+        h->perm.ensure(sizeof(int32_t) * n);
+        sort_segments(h, hj[0].col[D - 1], 1, n, std::vector<int>{(int)n}, h->perm.as<int32_t>());
+        hj[0].perm = h->perm.as<int32_t>();
+        ordered = true;
+    }
+    run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom, ordered);
     h->st.point_pairs += n * n;
     double v = 0.0;
     CU(cudaMemcpyAsync(&v, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -441,7 +554,25 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         }
         for (int64_t j = 0; j < nj; j++)
             for (int c = 0; c < D; c++) hj[j].col[c] = h->cols.as<double>() + (size_t)colidx[j * D + c] * stride;
-        run_jobs(h, hj, n_max, 1, 1, dz, o, out_dev + pos, false, nullptr, nullptr);
+        bool ordered = false;
+        if (want_sweep(o, 1, 1, dz, n_max)) {
+            // one argsort per distinct key column (the target's own past, last z column): shared by every source gene
+            std::vector<int> slot(specs.size(), -1), keyspec, keylen;
+            for (int64_t j = 0; j < nj; j++) {
+                const int sp = colidx[j * D + D - 1];
+                if (slot[sp] < 0) { slot[sp] = (int)keyspec.size(); keyspec.push_back(sp); keylen.push_back(hj[j].n); }
+            }
+            const int nk = (int)keyspec.size();
+            h->keys_in.ensure(sizeof(double) * nk * stride);
+            h->perm.ensure(sizeof(int32_t) * nk * stride);
+            for (int i = 0; i < nk; i++)       // device-to-device copies of the key columns into one contiguous block
+                CU(cudaMemcpyAsync(h->keys_in.as<double>() + (size_t)i * stride, h->cols.as<double>() + (size_t)keyspec[i] * stride,
+                                   sizeof(double) * keylen[i], cudaMemcpyDeviceToDevice, h->stream));
+            sort_segments(h, h->keys_in.as<double>(), nk, stride, keylen, h->perm.as<int32_t>());
+            for (int64_t j = 0; j < nj; j++) hj[j].perm = h->perm.as<int32_t>() + (size_t)slot[colidx[j * D + D - 1]] * stride;
+            ordered = true;
+        }
+        run_jobs(h, hj, n_max, 1, 1, dz, o, out_dev + pos, false, nullptr, nullptr, ordered);
         pos = end;
     }
     if (!out_is_device && n_jobs > 0) {
@@ -462,6 +593,12 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
         if (src[j] < 0 || src[j] >= h->cg || dst[j] < 0 || dst[j] >= h->cg) fail(SCRIBE_E_ARG, "gene index out of range");
     begin_call(h);
     const int64_t N = h->cc;
+    const bool ordered = want_sweep(o, 1, 1, 1, (int)N);
+    if (ordered && !h->permS_valid) {                    // argsort every gene's S row once per upload
+        h->permS.ensure(sizeof(int32_t) * h->cg * N);
+        sort_segments(h, h->S.as<double>(), (int)h->cg, N, std::vector<int>((size_t)h->cg, (int)N), h->permS.as<int32_t>());
+        h->permS_valid = true;
+    }
     double* out_dev = out;
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (3 * N * 8))));
@@ -486,7 +623,7 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
         CU(cudaMemcpyAsync(h->jobs.p, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
         h->st.h2d_bytes += sizeof(JobDesc) * nj;
         coupling_prep_kernel<<<(unsigned)nj, TPB, 0, h->stream>>>(h->S.as<double>(), h->Y.as<double>(), N,
-            h->idx32a.as<int32_t>() + pos, h->idx32b.as<int32_t>() + pos, drop_zero, h->cols.as<double>(), N,
+            ordered ? h->permS.as<int32_t>() : nullptr, h->idx32a.as<int32_t>() + pos, h->idx32b.as<int32_t>() + pos, drop_zero, h->cols.as<double>(), N,
             h->jobs.as<JobDesc>(), h->neff.as<int32_t>() + pos);
         CU(cudaGetLastError());
         h->st.kernel_launches++;
@@ -494,7 +631,11 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
         CU(cudaStreamSynchronize(h->stream));
         h->st.d2h_bytes += sizeof(int32_t) * nj;
         for (int64_t j = 0; j < nj; j++) h->st.point_pairs += (int64_t)neff_host[pos + j] * neff_host[pos + j];
-        run_jobs(h, hj, (int)N, 1, 1, 1, o, out_dev + pos, true, nullptr, nullptr);
+        run_jobs(h, hj, (int)N, 1, 1, 1, o, out_dev + pos, true, nullptr, nullptr, ordered);
+        if (!ordered) for (int64_t j = 0; j < nj; j++) {
+            const int64_t nn = (int64_t)neff_host[pos + j] * neff_host[pos + j];
+            h->st.visited_knn += nn; h->st.visited_count += nn;
+        }
     }
     if (n_eff) std::memcpy(n_eff, neff_host.data(), sizeof(int32_t) * n_jobs);
     if (!out_is_device && n_jobs > 0) {
@@ -553,7 +694,8 @@ void scribe_destroy(scribe_handle* h) {
     Guard g(h);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
-                      &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single})
+                      &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS})
         b->release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
     cudaStreamDestroy(h->stream);
@@ -632,7 +774,7 @@ int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, i
         CU(cudaMemcpyAsync(h->Y.p, Y, bytes, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         h->st.h2d_bytes = 2 * bytes;
-        h->cg = n_genes; h->cc = n_cells;
+        h->cg = n_genes; h->cc = n_cells; h->permS_valid = false;
         end_call(h);
     });
 }

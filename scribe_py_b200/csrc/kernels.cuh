@@ -28,7 +28,8 @@ constexpr int GEN_KCAP = 64;  // generic kernel: k+1 <= 64
 
 struct JobDesc {
     const double* col[MAXD];  // x dims, then y dims, then z dims
-    const double* w;          // uniformisation weights (cumi/umi) or nullptr
+    const double* w;          // uniformisation weights (cumi/umi) or nullptr; indexed like the columns
+    const int32_t* perm;      // sweep kernels: rank -> row index, rows sorted ascending by the LAST column (nullptr = identity)
     int64_t qoff;             // offset of this job's per-point outputs (eps/counts/...) in the workspace
     int32_t n;                // points
     int32_t pad;
@@ -287,6 +288,362 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
     if (tid == 0) partial[blockIdx.x] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sorted-sweep kernels.  Every subspace the conditional estimators count in (xyz, xz, yz, z) contains the
+// conditioning coordinates, so a candidate with |z_j - z_i| > eps_i can be in none of the balls -- and, for the
+// same reason, cannot be among the k nearest joint neighbours once the running k-th distance has dropped below
+// |z_j - z_i|.  The points of a job are therefore visited in the order of their last conditioning coordinate
+// (JobDesc.perm, one device sort per (target gene, lag) column, shared by every source gene that reads it).
+// A warp owns 32*Q consecutive ranks and sweeps outwards from them in chunks of 32 candidates, left and right,
+// until the nearest unvisited candidate on that side is too far in z for every one of its queries:
+//   pass 1 stops a side when fl(|z_i - z_next|) >= current k-th distance of every query (strict insert test),
+//   pass 2 stops a side when fl(|z_i - z_next|) >  eps_i for every query (closed ball),
+// both evaluated with the very subtraction the ball test uses, so by monotonicity of rounding the visited set is
+// an exact superset of what the dense kernel would have accepted: results are bit-identical to it.
+// No block-level synchronisation: warps are independent (chunks are staged in a per-warp shared-memory buffer).
+// ------------------------------------------------------------------------------------------------
+template <int D, bool WEIGHTED>
+struct Chunk { double v[D]; double w; };
+
+template <int D, bool WEIGHTED>
+__device__ __forceinline__ Chunk<D, WEIGHTED> load_chunk(const JobDesc& jd, int chunk, int lane, int n) {
+    Chunk<D, WEIGHTED> c;
+    const int rank = chunk * 32 + lane;
+    const bool ok = rank < n;
+    const int idx = ok ? (jd.perm ? jd.perm[rank] : rank) : 0;
+    #pragma unroll
+    for (int d = 0; d < D; d++) c.v[d] = ok ? jd.col[d][idx] : __longlong_as_double(0x7ff8000000000000LL);
+    c.w = 0.0;
+    if (WEIGHTED) c.w = ok ? jd.w[idx] : 0.0;
+    return c;
+}
+
+template <int DX, int DY, int DZ, int KCAP, int Q, bool WEIGHTED>
+__global__ void __launch_bounds__(TPB)
+ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
+                 double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
+{
+    constexpr int D = DX + DY + DZ;
+    constexpr int KEY = D - 1;
+    constexpr int W = TPB / 32;
+    __shared__ __align__(16) double sbuf[W][D + (WEIGHTED ? 1 : 0)][32];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int bpj = (warps_per_job + W - 1) / W;
+    const int job = blockIdx.x / bpj;
+    const int wj  = (blockIdx.x - job * bpj) * W + wid;          // warp index inside the job
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int w0 = wj * 32 * Q;
+    if (wj >= warps_per_job || w0 >= n) return;                  // warp-uniform; nothing below synchronises the CTA
+    const int c0 = w0 / 32;                                      // first centre chunk
+    const int nchunks = (n + 31) / 32;
+    double (*buf)[32] = sbuf[wid];
+
+    // queries = the centre chunks themselves (rank = w0 + q*32 + lane); idle slots shadow the last point
+    double qc[Q][D], qw[Q];
+    int qidx[Q]; bool qok[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int rank = w0 + q * 32 + lane;
+        qok[q] = rank < n;
+        const int rr = qok[q] ? rank : n - 1;
+        qidx[q] = jd.perm ? jd.perm[rr] : rr;
+        #pragma unroll
+        for (int d = 0; d < D; d++) qc[q][d] = jd.col[d][qidx[q]];
+        qw[q] = 0.0;
+        if (WEIGHTED) qw[q] = jd.w[qidx[q]];
+    }
+
+    auto stage = [&](const Chunk<D, WEIGHTED>& c) {              // registers -> this warp's buffer
+        __syncwarp();
+        #pragma unroll
+        for (int d = 0; d < D; d++) buf[d][lane] = c.v[d];
+        if (WEIGHTED) buf[D][lane] = c.w;
+        __syncwarp();
+    };
+    auto centre_chunk = [&](int q) {
+        Chunk<D, WEIGHTED> c;
+        #pragma unroll
+        for (int d = 0; d < D; d++) c.v[d] = qok[q] ? qc[q][d] : __longlong_as_double(0x7ff8000000000000LL);
+        c.w = qok[q] ? qw[q] : 0.0;
+        return c;
+    };
+
+    // ---------------- pass 1 ----------------
+    double L[Q][KCAP];
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
+
+    auto knn_chunk = [&]() {
+        #pragma unroll 2
+        for (int j = 0; j < 32; j += 2) {
+            double ad[2][Q][D];
+            bool lt[2][Q];
+            bool any = false;
+            #pragma unroll
+            for (int jj = 0; jj < 2; jj++)
+                #pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    bool l = true;
+                    #pragma unroll
+                    for (int d = 0; d < D; d++) { ad[jj][q][d] = fabs(qc[q][d] - buf[d][j + jj]); l = l & (ad[jj][q][d] < L[q][KCAP - 1]); }
+                    lt[jj][q] = l; any = any | l;
+                }
+            if (any) {
+                #pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+                    #pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        double dd = ad[jj][q][0];
+                        #pragma unroll
+                        for (int d = 1; d < D; d++) dd = fmax(dd, ad[jj][q][d]);
+                        if (lt[jj][q] && dd < L[q][KCAP - 1]) topk_insert<KCAP>(L[q], dd);
+                    }
+            }
+        }
+    };
+
+    unsigned long long nvis = 0, nvis2 = 0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { if (c0 + q < nchunks) { stage(centre_chunk(q)); knn_chunk(); nvis++; } }
+    {
+        int cl = c0 - 1, cr = c0 + Q;
+        Chunk<D, WEIGHTED> Lc, Rc;
+        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
+        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
+        while (true) {
+            bool nl = false, nr = false;
+            if (cl >= 0) {
+                const double zl = __shfl_sync(0xffffffffu, Lc.v[KEY], 31);
+                #pragma unroll
+                for (int q = 0; q < Q; q++) nl = nl | (fabs(qc[q][KEY] - zl) < L[q][KCAP - 1]);
+                nl = __any_sync(0xffffffffu, nl);
+            }
+            if (cr < nchunks) {
+                const double zr = __shfl_sync(0xffffffffu, Rc.v[KEY], 0);
+                #pragma unroll
+                for (int q = 0; q < Q; q++) nr = nr | (fabs(qc[q][KEY] - zr) < L[q][KCAP - 1]);
+                nr = __any_sync(0xffffffffu, nr);
+            }
+            if (!nl && !nr) break;
+            if (nl) { stage(Lc); --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); knn_chunk(); nvis++; }
+            if (nr) { stage(Rc); ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); knn_chunk(); nvis++; }
+        }
+    }
+
+    double eps[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) eps[q] = L[q][KCAP - 1];
+
+    // ---------------- pass 2 ----------------
+    int nxyz[Q], nxz[Q], nyz[Q], nz[Q];
+    double wyz[Q], wz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
+
+    auto count_chunk = [&]() {
+        #pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            double cc[D];
+            #pragma unroll
+            for (int d = 0; d < D; d++) cc[d] = buf[d][j];
+            double wj_ = 0.0;
+            if (WEIGHTED) wj_ = buf[D][j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                bool pz = true, px = true, py = true;
+                #pragma unroll
+                for (int d = 0; d < DZ; d++) pz = pz & (fabs(qc[q][DX + DY + d] - cc[DX + DY + d]) <= eps[q]);
+                #pragma unroll
+                for (int d = 0; d < DX; d++) px = px & (fabs(qc[q][d] - cc[d]) <= eps[q]);
+                #pragma unroll
+                for (int d = 0; d < DY; d++) py = py & (fabs(qc[q][DX + d] - cc[DX + d]) <= eps[q]);
+                const bool pxz = px & pz, pyz = py & pz, pxyz = pxz & py;
+                inc_if(nz[q], pz); inc_if(nxz[q], pxz); inc_if(nyz[q], pyz); inc_if(nxyz[q], pxyz);
+                if (WEIGHTED) { add_if(wz[q], wj_, pz); add_if(wyz[q], wj_, pyz); }
+            }
+        }
+    };
+
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { if (c0 + q < nchunks) { stage(centre_chunk(q)); count_chunk(); nvis2++; } }
+    {
+        int cl = c0 - 1, cr = c0 + Q;
+        Chunk<D, WEIGHTED> Lc, Rc;
+        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
+        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
+        while (true) {
+            bool nl = false, nr = false;
+            if (cl >= 0) {
+                const double zl = __shfl_sync(0xffffffffu, Lc.v[KEY], 31);
+                #pragma unroll
+                for (int q = 0; q < Q; q++) nl = nl | (fabs(qc[q][KEY] - zl) <= eps[q]);
+                nl = __any_sync(0xffffffffu, nl);
+            }
+            if (cr < nchunks) {
+                const double zr = __shfl_sync(0xffffffffu, Rc.v[KEY], 0);
+                #pragma unroll
+                for (int q = 0; q < Q; q++) nr = nr | (fabs(qc[q][KEY] - zr) <= eps[q]);
+                nr = __any_sync(0xffffffffu, nr);
+            }
+            if (!nl && !nr) break;
+            if (nl) { stage(Lc); --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); count_chunk(); nvis2++; }
+            if (nr) { stage(Rc); ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); count_chunk(); nvis2++; }
+        }
+    }
+
+    // ---------------- digamma terms + per-warp partial (fixed shuffle tree) ----------------
+    double acc = 0.0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        if (qok[q]) {
+            const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
+            const int64_t o = jd.qoff + qidx[q];
+            double term;
+            if (WEIGHTED) {
+                const double wi = qw[q];
+                const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
+                term = wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
+                if (po.wsum) { po.wsum[2 * o] = Wyz; po.wsum[2 * o + 1] = Wz; }
+            } else {
+                term = psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            }
+            acc += term;
+            if (po.eps) po.eps[o] = eps[q];
+            if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        partial[(size_t)job * warps_per_job + wj] = acc;
+        if (visited) { atomicAdd(visited, nvis * 32ull * 32ull * Q); atomicAdd(visited + 1, nvis2 * 32ull * 32ull * Q); }
+    }
+}
+
+// Gaussian KDE inverse densities, sorted sweep: terms with (z_i - z_j)^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
+// than 2^-KDE_CUT each against a sum that is >= 1 (the self term), so a side is abandoned once the nearest unvisited
+// candidate is that far in the key coordinate for every query of the warp.
+constexpr double KDE_CUT = 64.0;
+
+template <int DP, int Q>
+__global__ void __launch_bounds__(TPB)
+kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int* __restrict__ dims, double scale,
+                 double* __restrict__ u_out, unsigned long long* __restrict__ visited)
+{
+    constexpr int W = TPB / 32;
+    constexpr int KEY = DP - 1;                                   // dims[] lists the key column last
+    __shared__ __align__(16) double sbuf[W][DP][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int bpj = (warps_per_job + W - 1) / W;
+    const int job = blockIdx.x / bpj;
+    const int wj  = (blockIdx.x - job * bpj) * W + wid;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int w0 = wj * 32 * Q;
+    if (wj >= warps_per_job || w0 >= n) return;
+    const int c0 = w0 / 32, nchunks = (n + 31) / 32;
+    double (*buf)[32] = sbuf[wid];
+    const double* cp[DP];
+    #pragma unroll
+    for (int d = 0; d < DP; d++) cp[d] = jd.col[dims[d]];
+    const double rcut = sqrt(KDE_CUT);                            // in scaled units
+
+    auto load = [&](int chunk, double (&v)[DP]) {
+        const int rank = chunk * 32 + lane;
+        const bool ok = rank < n;
+        const int idx = ok ? (jd.perm ? jd.perm[rank] : rank) : 0;
+        #pragma unroll
+        for (int d = 0; d < DP; d++) v[d] = ok ? cp[d][idx] * scale : INFINITY;     // exp2(-inf) = 0
+    };
+    auto stage = [&](const double (&v)[DP]) {
+        __syncwarp();
+        #pragma unroll
+        for (int d = 0; d < DP; d++) buf[d][lane] = v[d];
+        __syncwarp();
+    };
+
+    double qc[Q][DP]; int qidx[Q]; bool qok[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int rank = w0 + q * 32 + lane;
+        qok[q] = rank < n;
+        const int rr = qok[q] ? rank : n - 1;
+        qidx[q] = jd.perm ? jd.perm[rr] : rr;
+        #pragma unroll
+        for (int d = 0; d < DP; d++) qc[q][d] = cp[d][qidx[q]] * scale;
+    }
+    double S[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) S[q] = 0.0;
+
+    auto kde_chunk = [&]() {
+        float s32[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) s32[q] = 0.f;
+        #pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                double d2 = 0.0;
+                #pragma unroll
+                for (int d = 0; d < DP; d++) { const double df = qc[q][d] - buf[d][j]; d2 = fma(df, df, d2); }
+                float e;
+                const float a = -(float)d2;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+                s32[q] += e;
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) S[q] += (double)s32[q];
+    };
+
+    unsigned long long nvis = 0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        if (c0 + q < nchunks) {
+            double v[DP];
+            #pragma unroll
+            for (int d = 0; d < DP; d++) v[d] = qok[q] ? qc[q][d] : INFINITY;
+            stage(v); kde_chunk(); nvis++;
+        }
+    }
+    int cl = c0 - 1, cr = c0 + Q;
+    double Lv[DP], Rv[DP];
+    if (cl >= 0) load(cl, Lv);
+    if (cr < nchunks) load(cr, Rv);
+    while (true) {
+        bool nl = false, nr = false;
+        if (cl >= 0) {
+            const double zl = __shfl_sync(0xffffffffu, Lv[KEY], 31);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) nl = nl | (fabs(qc[q][KEY] - zl) <= rcut);
+            nl = __any_sync(0xffffffffu, nl);
+        }
+        if (cr < nchunks) {
+            const double zr = __shfl_sync(0xffffffffu, Rv[KEY], 0);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) nr = nr | (fabs(qc[q][KEY] - zr) <= rcut);
+            nr = __any_sync(0xffffffffu, nr);
+        }
+        if (!nl && !nr) break;
+        if (nl) { stage(Lv); --cl; if (cl >= 0) load(cl, Lv); kde_chunk(); nvis++; }
+        if (nr) { stage(Rv); ++cr; if (cr < nchunks) load(cr, Rv); kde_chunk(); nvis++; }
+    }
+    #pragma unroll
+    for (int q = 0; q < Q; q++) if (qok[q]) u_out[jd.qoff + qidx[q]] = 1.0 / S[q];
+    if (lane == 0 && visited) atomicAdd(visited + 2, nvis * 32ull * 32ull * Q);
+}
+
+__global__ void iota_segments_kernel(int32_t* __restrict__ v, int64_t stride, int n_seg) {
+    const int64_t total = stride * n_seg;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = (int32_t)(i % stride);
+}
+
 // out[job] = (sum of that job's CTA partials, in CTA order) / n      (np.mean at :109,:173,:403)
 __global__ void finalize_mean_kernel(const JobDesc* __restrict__ jobs, const double* __restrict__ partial,
                                      int blocks_per_job, int n_jobs, double* __restrict__ out)
@@ -532,11 +889,14 @@ gather_lagged_kernel(const double* __restrict__ E, int64_t n_cells, const int64_
 
 // ------------------------------------------------------------------------------------------------
 // dynamics-coupling prep (replaces Scribe.py:119-133): per job gather x = S[src], y = Y[dst], z = S[dst],
-// keep cells with (x + y) + z > 0 (float64, this association order) and compact them stably.
+// keep cells with (x + y) + z > 0 (float64, this association order) and compact them stably -- visiting the cells
+// in the target's z-sorted order when permS is given, so the compacted columns come out sorted for the sweep kernels
+// (the estimate does not depend on the order of the samples).
 // One CTA per job; writes 3 columns of stride `col_stride` and the kept count into jobs[job].n.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB)
 coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y, int64_t n_cells,
+                     const int32_t* __restrict__ permS,   // [G][n_cells]: cells of each gene sorted by S (or nullptr)
                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int drop_zero,
                      double* __restrict__ cols, int64_t col_stride, JobDesc* __restrict__ jobs, int32_t* __restrict__ n_eff)
 {
@@ -553,10 +913,11 @@ coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y,
     if (tid == 0) base_s = 0;
     __syncthreads();
     for (int64_t c0 = 0; c0 < n_cells; c0 += TPB) {
-        const int64_t c = c0 + tid;
+        const int64_t r = c0 + tid;                      // rank in the target's z-sorted order (or plain cell index)
         double x = 0, y = 0, z = 0;
         bool keep = false;
-        if (c < n_cells) {
+        if (r < n_cells) {
+            const int64_t c = permS ? permS[(size_t)dst[job] * n_cells + r] : r;
             x = xs[c]; y = ys[c]; z = zs[c];
             keep = drop_zero ? (__dadd_rn(__dadd_rn(x, y), z) > 0.0) : true;
         }

@@ -31,7 +31,7 @@ def test_header_symbols_exported():
 def test_struct_layouts():
     assert ctypes.sizeof(_lib.Opts) == 32
     assert _lib.JOB_DTYPE.itemsize == 48
-    assert ctypes.sizeof(_lib.Stats) == 64
+    assert ctypes.sizeof(_lib.Stats) == 88
 
 
 def _has_gpu():

@@ -28,7 +28,7 @@ def close(got, ref, tol):
     return abs(got - ref) <= tol
 
 
-@pytest.mark.parametrize("path", ["auto", "generic"])
+@pytest.mark.parametrize("path", ["auto", "generic", "dense", "sweep"])
 @pytest.mark.parametrize("name", list(SETS))
 def test_counts_bit_exact(S, golden, name, path):
     x, y, z = SETS[name]()
@@ -101,17 +101,30 @@ def test_error_behaviour(S):
     assert S.vd(3) == pytest.approx(o.vd(3), abs=1e-15)
 
 
-def test_random_sizes_against_oracle(S):
-    """ragged sizes around the tile / CTA boundaries, continuous and tied data"""
+@pytest.mark.parametrize("path", ["dense", "sweep"])
+def test_random_sizes_against_oracle(S, path):
+    """ragged sizes around the chunk / tile / CTA boundaries, continuous x,y and heavily tied z"""
     rng = np.random.default_rng(5)
-    for n in (1, 2, 255, 256, 257, 511, 512, 513, 1025, 1537):
+    for n in (1, 2, 31, 32, 33, 63, 64, 65, 255, 256, 257, 511, 512, 513, 1025, 1537, 2049, 4100):
         x = rng.standard_normal((n, 1)); z = np.round(rng.standard_normal((n, 1)), 1); y = x + z + rng.standard_normal((n, 1))
-        d = S.information_estimators.ksg_debug("cmi", x, y, z)
+        d = S.information_estimators.ksg_debug("cmi", x, y, z, path=path)
         eps, cnt = o.cmi_debug(x, y, z)
         assert np.array_equal(d["eps"], eps), n
         assert np.array_equal(d["counts"], cnt), n
         got, ref = S.cmi(x, y, z), o.cmi(x, y, z)
         assert close(got, ref, TOL_EXACT) or (np.isinf(ref) and got == ref), n
+
+
+@pytest.mark.parametrize("name", ["a", "b", "poisson", "d5"])
+def test_sweep_equals_dense_uniformised(S, name):
+    """the sorted sweep must reproduce the dense kernels: eps/counts bit for bit, weights and weighted sums to 1e-12
+    (the KDE sweep drops terms below 2^-64 of a sum that is >= 1)"""
+    x, y, z = SETS[name]()
+    a = S.information_estimators.ksg_debug("cumi", x, y, z, path="dense")
+    b = S.information_estimators.ksg_debug("cumi", x, y, z, path="sweep")
+    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    assert np.allclose(a["weights"], b["weights"], rtol=1e-6, atol=0)
+    assert np.allclose(a["wsum"], b["wsum"], rtol=1e-6, atol=0)
 
 
 def test_dynamics_coupling_c1(S, golden):
@@ -198,8 +211,9 @@ def test_full_size_properties(S):
     assert (c[0] >= 5).all() and (c[0] == 5).mean() > 0.99
     assert (c[0] <= c[1]).all() and (c[0] <= c[2]).all() and (c[1] <= c[3]).all() and (c[2] <= c[3]).all()
     assert (c[3] <= len(x) - 1).all()
-    g = S.information_estimators.ksg_debug("cmi", x, y, z, path="generic")
-    assert np.array_equal(g["eps"], d["eps"]) and np.array_equal(g["counts"], c)
+    for path in ("generic", "dense", "sweep"):
+        g = S.information_estimators.ksg_debug("cmi", x, y, z, path=path)
+        assert np.array_equal(g["eps"], d["eps"]) and np.array_equal(g["counts"], c), path
     perm = np.random.default_rng(0).permutation(len(x))
     v0, v1 = S.cmi(x, y, z), S.cmi(x[perm], y[perm], z[perm])
     assert abs(v0 - v1) < 1e-12

@@ -27,6 +27,8 @@ def run(G, T, delays, est, reps=2):
     pairs = best["point_pairs"]
     clk = 1.965e9
     cps = best["estimator_ms"] * 1e-3 * clk * 148 * 4 / (pairs / 32)        # SMSP-cycles per warp-step (32 point pairs)
+    vis = (best["visited_knn"] + best["visited_count"]) / (2.0 * pairs)
+    print("path=%s vis=%.3f clk/visited-step=%.1f " % (os.environ.get("SCRIBE_B200_PATH", "auto"), vis, cps / max(vis, 1e-9)), end="")
     print("Q=%s est=%d G=%d T=%d jobs=%d  est_ms=%.2f total_ms=%.2f  evals/s=%.0f  pairs/s=%.3e  clk/warp-step=%.2f  checksum=%.12f"
           % (os.environ.get("SCRIBE_B200_Q", "auto"), est, G, T, len(jobs), best["estimator_ms"], best["total_ms"],
              len(jobs) / (best["total_ms"] * 1e-3), pairs / (best["estimator_ms"] * 1e-3), cps, float(np.nansum(v))), flush=True)
