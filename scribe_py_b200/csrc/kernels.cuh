@@ -362,12 +362,41 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
         if (WEIGHTED) buf[D][lane] = c.w;
         __syncwarp();
     };
-    auto centre_chunk = [&](int q) {
-        Chunk<D, WEIGHTED> c;
-        #pragma unroll
-        for (int d = 0; d < D; d++) c.v[d] = qok[q] ? qc[q][d] : __longlong_as_double(0x7ff8000000000000LL);
-        c.w = qok[q] ? qw[q] : 0.0;
-        return c;
+    // Outward sweep shared by both passes: the centre chunks first, then whichever side still has a candidate that
+    // some query of the warp needs (need(z_next) is the per-lane test), alternating when both do.  One call site
+    // for the per-chunk work keeps the unrolled bodies from being replicated.
+    auto sweep = [&](auto need, auto work) -> unsigned long long {
+        unsigned long long visits = 0;
+        int cl = c0 - 1, cr = c0 + Q, centre = 0;
+        bool toggle = false;
+        Chunk<D, WEIGHTED> Lc, Rc, cur;
+        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
+        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
+        while (true) {
+            if (centre < Q) {
+                if (c0 + centre >= nchunks) { centre = Q; continue; }    // last warp of a job: fewer centre chunks, the left side remains
+                #pragma unroll
+                for (int q = 0; q < Q; q++) if (q == centre) {
+                    #pragma unroll
+                    for (int d = 0; d < D; d++) cur.v[d] = qok[q] ? qc[q][d] : __longlong_as_double(0x7ff8000000000000LL);
+                    cur.w = qok[q] ? qw[q] : 0.0;
+                }
+                ++centre;
+            } else {
+                bool nl = false, nr = false;
+                if (cl >= 0)      nl = __any_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Lc.v[KEY], 31)));
+                if (cr < nchunks) nr = __any_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Rc.v[KEY], 0)));
+                if (!nl && !nr) break;
+                const bool left = nl && (!nr || toggle);
+                toggle = !toggle;
+                if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
+                else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
+            }
+            stage(cur);
+            work();
+            ++visits;
+        }
+        return visits;
     };
 
     // ---------------- pass 1 ----------------
@@ -377,62 +406,46 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
         #pragma unroll
         for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
 
+    // Per chunk: (i) a branch-free scan marks, per query, which of the 32 candidates beat the k-th distance the query
+    // had when the chunk started (one bit each); (ii) the marked candidates are then inserted in a short per-lane loop.
+    // Inside the z-window nearly every warp-step would otherwise contain some lane that inserts (the number of inserts per
+    // query, ~ (k+1) ln(window), does not shrink with the window), so batching them per chunk is what keeps the
+    // divergent insert path off the scan.
     auto knn_chunk = [&]() {
-        #pragma unroll 2
-        for (int j = 0; j < 32; j += 2) {
-            double ad[2][Q][D];
-            bool lt[2][Q];
-            bool any = false;
+        unsigned mask[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) mask[q] = 0u;
+        #pragma unroll
+        for (int j = 0; j < 32; j++) {
+            double cc[D];
             #pragma unroll
-            for (int jj = 0; jj < 2; jj++)
+            for (int d = 0; d < D; d++) cc[d] = buf[d][j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                bool l = true;
                 #pragma unroll
-                for (int q = 0; q < Q; q++) {
-                    bool l = true;
-                    #pragma unroll
-                    for (int d = 0; d < D; d++) { ad[jj][q][d] = fabs(qc[q][d] - buf[d][j + jj]); l = l & (ad[jj][q][d] < L[q][KCAP - 1]); }
-                    lt[jj][q] = l; any = any | l;
-                }
-            if (any) {
+                for (int d = 0; d < D; d++) l = l & (fabs(qc[q][d] - cc[d]) < L[q][KCAP - 1]);
+                asm("{.reg .pred p; setp.ne.b32 p, %1, 0; @p or.b32 %0, %0, %2;}" : "+r"(mask[q]) : "r"((int)l), "r"(1u << j));
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            while (mask[q]) {
+                const int j = __ffs(mask[q]) - 1;
+                mask[q] &= mask[q] - 1;
+                double dd = fabs(qc[q][0] - buf[0][j]);
                 #pragma unroll
-                for (int jj = 0; jj < 2; jj++)
-                    #pragma unroll
-                    for (int q = 0; q < Q; q++) {
-                        double dd = ad[jj][q][0];
-                        #pragma unroll
-                        for (int d = 1; d < D; d++) dd = fmax(dd, ad[jj][q][d]);
-                        if (lt[jj][q] && dd < L[q][KCAP - 1]) topk_insert<KCAP>(L[q], dd);
-                    }
+                for (int d = 1; d < D; d++) dd = fmax(dd, fabs(qc[q][d] - buf[d][j]));
+                if (dd < L[q][KCAP - 1]) topk_insert<KCAP>(L[q], dd);          // the bar may have moved since the scan
             }
         }
     };
-
-    unsigned long long nvis = 0, nvis2 = 0;
-    #pragma unroll
-    for (int q = 0; q < Q; q++) { if (c0 + q < nchunks) { stage(centre_chunk(q)); knn_chunk(); nvis++; } }
-    {
-        int cl = c0 - 1, cr = c0 + Q;
-        Chunk<D, WEIGHTED> Lc, Rc;
-        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
-        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
-        while (true) {
-            bool nl = false, nr = false;
-            if (cl >= 0) {
-                const double zl = __shfl_sync(0xffffffffu, Lc.v[KEY], 31);
-                #pragma unroll
-                for (int q = 0; q < Q; q++) nl = nl | (fabs(qc[q][KEY] - zl) < L[q][KCAP - 1]);
-                nl = __any_sync(0xffffffffu, nl);
-            }
-            if (cr < nchunks) {
-                const double zr = __shfl_sync(0xffffffffu, Rc.v[KEY], 0);
-                #pragma unroll
-                for (int q = 0; q < Q; q++) nr = nr | (fabs(qc[q][KEY] - zr) < L[q][KCAP - 1]);
-                nr = __any_sync(0xffffffffu, nr);
-            }
-            if (!nl && !nr) break;
-            if (nl) { stage(Lc); --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); knn_chunk(); nvis++; }
-            if (nr) { stage(Rc); ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); knn_chunk(); nvis++; }
-        }
-    }
+    const unsigned long long nvis = sweep(
+        [&](double znext) { bool f = false;
+                            #pragma unroll
+                            for (int q = 0; q < Q; q++) f = f | (fabs(qc[q][KEY] - znext) < L[q][KCAP - 1]);
+                            return f; },
+        knn_chunk);
 
     double eps[Q];
     #pragma unroll
@@ -467,33 +480,12 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             }
         }
     };
-
-    #pragma unroll
-    for (int q = 0; q < Q; q++) { if (c0 + q < nchunks) { stage(centre_chunk(q)); count_chunk(); nvis2++; } }
-    {
-        int cl = c0 - 1, cr = c0 + Q;
-        Chunk<D, WEIGHTED> Lc, Rc;
-        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
-        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
-        while (true) {
-            bool nl = false, nr = false;
-            if (cl >= 0) {
-                const double zl = __shfl_sync(0xffffffffu, Lc.v[KEY], 31);
-                #pragma unroll
-                for (int q = 0; q < Q; q++) nl = nl | (fabs(qc[q][KEY] - zl) <= eps[q]);
-                nl = __any_sync(0xffffffffu, nl);
-            }
-            if (cr < nchunks) {
-                const double zr = __shfl_sync(0xffffffffu, Rc.v[KEY], 0);
-                #pragma unroll
-                for (int q = 0; q < Q; q++) nr = nr | (fabs(qc[q][KEY] - zr) <= eps[q]);
-                nr = __any_sync(0xffffffffu, nr);
-            }
-            if (!nl && !nr) break;
-            if (nl) { stage(Lc); --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); count_chunk(); nvis2++; }
-            if (nr) { stage(Rc); ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); count_chunk(); nvis2++; }
-        }
-    }
+    const unsigned long long nvis2 = sweep(
+        [&](double znext) { bool f = false;
+                            #pragma unroll
+                            for (int q = 0; q < Q; q++) f = f | (fabs(qc[q][KEY] - znext) <= eps[q]);
+                            return f; },
+        count_chunk);
 
     // ---------------- digamma terms + per-warp partial (fixed shuffle tree) ----------------
     double acc = 0.0;
