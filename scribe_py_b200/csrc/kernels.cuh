@@ -302,6 +302,9 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
 // an exact superset of what the dense kernel would have accepted: results are bit-identical to it.
 // No block-level synchronisation: warps are independent (chunks are staged in a per-warp shared-memory buffer).
 // ------------------------------------------------------------------------------------------------
+#ifndef SWEEP_MIN_CTAS
+#define SWEEP_MIN_CTAS 3
+#endif
 template <int D, bool WEIGHTED>
 struct Chunk { double v[D]; double w; };
 
@@ -319,7 +322,7 @@ __device__ __forceinline__ Chunk<D, WEIGHTED> load_chunk(const JobDesc& jd, int 
 }
 
 template <int DX, int DY, int DZ, int KCAP, int Q, bool WEIGHTED>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, SWEEP_MIN_CTAS)
 ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                  double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {

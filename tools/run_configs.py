@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Throughput and sampled parity of every named BASELINE.json config on one GPU.
+
+    python tools/run_configs.py [c1 c2 c3 c4 c5] [--scale S]   (S < 1 shrinks the gene count of the big configs)
+
+For each config: GPU wall time through the public API, evaluations/s, device time of the estimator kernels, the
+fraction of dense point pairs the sorted sweep visits, and the max |difference| against the reference-shaped CPU port
+(oracle/ref_port.py) on a few sampled jobs.  Writes one JSON line per config."""
+import argparse, json, os, sys, time, warnings
+import numpy as np, pandas as pd
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import recipes
+import scribe_py_b200 as S
+from scribe_py_b200 import _lib
+from oracle import ref_port, ksg_oracle
+
+
+def ar_panel(G, T, seed):
+    """cheap autocorrelated expression panel with sparse lagged couplings (vectorised over genes)"""
+    rng = np.random.default_rng(seed)
+    E = np.zeros((G, T + 60)); E[:, :12] = rng.standard_normal((G, 12))
+    par = rng.integers(0, G, (G, 2)); dl = rng.choice([1, 5, 10], (G, 2)); co = rng.uniform(0.4, 0.9, (G, 2)) * rng.choice([-1, 1], (G, 2))
+    noise = 0.3 * rng.standard_normal((G, T + 60))
+    for t in range(12, T + 60):
+        E[:, t] = 0.9 * E[:, t - 1] + noise[:, t] + co[:, 0] * np.tanh(E[par[:, 0], t - dl[:, 0]]) + co[:, 1] * np.tanh(E[par[:, 1], t - dl[:, 1]])
+    return E[:, 60:]
+
+
+def cpu_check(fn, argsets):
+    from multiprocessing import get_context
+    with get_context("fork").Pool(min(len(argsets), os.cpu_count() or 1)) as p:
+        return np.array(p.map(fn, argsets))
+
+
+def _cmi_job(a):
+    return ref_port.cmi(*a)
+
+
+def _cumi_job(a):
+    return ref_port.cumi(*a)
+
+
+def report(name, n_jobs, wall, stats, extra):
+    line = {"config": name, "jobs": int(n_jobs), "wall_s": wall, "evals_per_s": n_jobs / wall}
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def stats_acc():
+    return {"estimator_ms": 0.0, "point_pairs": 0, "visited_knn": 0, "visited_count": 0, "visited_kde": 0, "kernel_launches": 0}
+
+
+def run_c1():
+    spl, vel, genes = recipes.gv_c()
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, genes)
+    S.causal_net_dynamics_coupling(ad)              # warm-up
+    t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); wall = time.perf_counter() - t
+    M = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
+    ref = ksg_oracle.dynamics_coupling(spl, vel)
+    st = _lib.default_handle().stats()
+    return report("C1 dynamics coupling 20 genes x 500 cells", 380, wall, st,
+                  {"parity_max_abs_diff": float(np.abs(M - ref).max()), "parity_jobs": 380, "estimator_ms": st["estimator_ms"]})
+
+
+def run_rdi(name, G, T, delays, uniform, seed, n_check, L=None):
+    E = ar_panel(G, T, seed)
+    if uniform:
+        E = (E - E.mean(1, keepdims=True)) / E.std(1, keepdims=True)
+    genes = ["g%04d" % i for i in range(G)]
+    m = S.causal_model(pd.DataFrame(E, index=pd.Index(genes, name="GENE_ID")))
+    h = _lib.default_handle()
+    t = time.perf_counter(); r = m.rdi(delays, uniformization=uniform); wall = time.perf_counter() - t
+    st = h.stats()
+    n_jobs = G * (G - 1) * len(delays)
+    rng = np.random.default_rng(0)
+    args, got = [], []
+    for _ in range(n_check):
+        a, b = rng.choice(G, 2, replace=False); d = delays[rng.integers(len(delays))]
+        x, y, z = ksg_oracle.lagged_columns([E[a]], [E[b]], d)
+        args.append((x, y, z)); got.append(r[d].iloc[a, b])
+    ref = cpu_check(_cumi_job if uniform else _cmi_job, args)
+    extra = {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+             "estimator_ms": st["estimator_ms"], "visited_fraction": (st["visited_knn"] + st["visited_count"]) / max(2 * st["point_pairs"], 1),
+             "note": "stats of the last chunk-call only" if False else ""}
+    out = [report(name, n_jobs, wall, st, extra)]
+    if L:
+        t = time.perf_counter(); c = m.crdi(L=L, uniformization=uniform); wall = time.perf_counter() - t
+        st = h.stats()
+        # parity of sampled cRDI jobs through the oracle's conditioning-set logic
+        res = {d: r[d].to_numpy(dtype=float) for d in delays}
+        val, arg = ksg_oracle.max_over_delays(res, delays)
+        jobs = ksg_oracle.crdi_jobs(val, arg, L)
+        expr = [[E[g]] for g in range(G)]
+        args, got = [], []
+        for _ in range(n_check):
+            a, b = rng.choice(G, 2, replace=False)
+            d, cn, cd = jobs[(int(a), int(b))]
+            args.append(ksg_oracle.crdi_columns(expr, int(a), int(b), d, cn, cd)); got.append(c.iloc[a, b])
+        ref = cpu_check(_cumi_job if uniform else _cmi_job, args)
+        out.append(report(name + " -> crdi(L=%d)" % L, G * (G - 1), wall, st,
+                          {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+                           "estimator_ms": st["estimator_ms"],
+                           "visited_fraction": (st["visited_knn"] + st["visited_count"]) / max(2 * st["point_pairs"], 1)}))
+    return out
+
+
+def run_c3(G, N, n_check):
+    rng = np.random.default_rng(3)
+    spl = rng.gamma(2., 1., (N, G)); spl[rng.random((N, G)) < 0.2] = 0
+    par = rng.integers(0, G, (G, 2)); co = rng.uniform(-0.5, 0.5, (G, 2))
+    vel = co[:, 0] * (spl[:, par[:, 0]] - spl[:, par[:, 0]].mean(0)) + co[:, 1] * (spl[:, par[:, 1]] - spl[:, par[:, 1]].mean(0)) \
+        - 0.2 * spl + 0.1 * rng.standard_normal((N, G))
+    genes = ["g%04d" % i for i in range(G)]
+    ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
+    h = _lib.default_handle()
+    t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); wall = time.perf_counter() - t
+    st = h.stats()
+    M = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
+    s = (spl - spl.mean(0)) / (spl.max(0) - spl.min(0)); v = (vel - vel.mean(0)) / (vel.max(0) - vel.min(0))
+    args, got = [], []
+    for _ in range(n_check):
+        a, b = rng.choice(G, 2, replace=False)
+        x, z = s[:, a], s[:, b]; y = s[:, b] + v[:, b]
+        keep = ((x + y) + z) > 0
+        args.append((x[keep], y[keep], z[keep])); got.append(M[a, b])
+    ref = cpu_check(_cmi_job, args)
+    return report("C3 dynamics coupling %d genes x %d cells" % (G, N), G * (G - 1), wall, st,
+                  {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+                   "estimator_ms_last_chunk": st["estimator_ms"], "mean_cells_kept": float(np.mean([len(a[0]) for a in args]))})
+
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore")
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    sc = a.scale
+    lines = []
+    h = _lib.default_handle()
+    print(json.dumps({"device": h.device_name, "sms": h.sm_count, "path": os.environ.get("SCRIBE_B200_PATH", "auto")}), flush=True)
+    for c in a.configs:
+        if c == "c1": lines.append(run_c1())
+        if c == "c2": lines += run_rdi("C2 RDI 100 genes x 2000 cells x delays {1,5,10}", 100, 2000, [1, 5, 10], False, 2, 32)
+        if c == "c3": lines.append(run_c3(max(8, int(500 * sc)), 10000, 16))
+        if c == "c4": lines += run_rdi("C4 RDI+cRDI(L=2) %d genes x 5000 cells" % max(8, int(200 * sc)), max(8, int(200 * sc)), 5000, [1, 5, 10], False, 4, 16, L=2)
+        if c == "c5": lines += run_rdi("C5 uniformised RDI (cumi) %d genes x 20000 cells x 3 delays" % max(8, int(1000 * sc)), max(8, int(1000 * sc)), 20000, [1, 5, 10], True, 5, 4)
+    if a.out:
+        with open(a.out, "w") as f:
+            for l in lines:
+                f.write(json.dumps(l) + "\n")
