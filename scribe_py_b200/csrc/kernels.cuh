@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <type_traits>
 
 namespace scribe {
 
@@ -365,40 +366,37 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
         if (WEIGHTED) buf[D][lane] = c.w;
         __syncwarp();
     };
-    // Outward sweep shared by both passes: the centre chunks first, then whichever side still has a candidate that
-    // some query of the warp needs (need(z_next) is the per-lane test), alternating when both do.  One call site
-    // for the per-chunk work keeps the unrolled bodies from being replicated.
+    // Sweep shared by both passes: the warp's own chunks first, then outwards, taking whichever side still has a
+    // candidate that some query of the warp needs (need(z_next) -> bit q set when this lane's query in slot q needs it),
+    // alternating when both sides do.  After regroup() below, slot Q-1 holds the warp's sparsest queries (largest
+    // eps), so the far part of the sweep is needed by that slot only: work(false) then skips the other slots.
     auto sweep = [&](auto need, auto work) -> unsigned long long {
         unsigned long long visits = 0;
-        int cl = c0 - 1, cr = c0 + Q, centre = 0;
+        int cl = c0 - 1, cr = c0 + Q;
         bool toggle = false;
         Chunk<D, WEIGHTED> Lc, Rc, cur;
         if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
         if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
         while (true) {
-            if (centre < Q) {
-                if (c0 + centre >= nchunks) { centre = Q; continue; }    // last warp of a job: fewer centre chunks, the left side remains
-                #pragma unroll
-                for (int q = 0; q < Q; q++) if (q == centre) {
-                    #pragma unroll
-                    for (int d = 0; d < D; d++) cur.v[d] = qok[q] ? qc[q][d] : __longlong_as_double(0x7ff8000000000000LL);
-                    cur.w = qok[q] ? qw[q] : 0.0;
-                }
-                ++centre;
-            } else {
-                bool nl = false, nr = false;
-                if (cl >= 0)      nl = __any_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Lc.v[KEY], 31)));
-                if (cr < nchunks) nr = __any_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Rc.v[KEY], 0)));
-                if (!nl && !nr) break;
-                const bool left = nl && (!nr || toggle);
-                toggle = !toggle;
-                if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
-                else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
-            }
+            unsigned al = 0, ar = 0;
+            if (cl >= 0)      al = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Lc.v[KEY], 31)));
+            if (cr < nchunks) ar = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Rc.v[KEY], 0)));
+            if (!al && !ar) break;
+            const bool left = al && (!ar || toggle);
+            toggle = !toggle;
+            const unsigned act = left ? al : ar;
+            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
+            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
             stage(cur);
-            work();
-            ++visits;
+            const bool all = (act & ((1u << (Q - 1)) - 1u)) != 0u || Q == 1;
+            work(all);
+            visits += all ? Q : 1;
         }
+        return visits;
+    };
+    auto centre = [&](auto work) -> unsigned long long {
+        unsigned long long visits = 0;
+        for (int c = c0; c < c0 + Q && c < nchunks; c++) { stage(load_chunk<D, WEIGHTED>(jd, c, lane, n)); work(true); visits += Q; }
         return visits;
     };
 
@@ -414,25 +412,27 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
     // Inside the z-window nearly every warp-step would otherwise contain some lane that inserts (the number of inserts per
     // query, ~ (k+1) ln(window), does not shrink with the window), so batching them per chunk is what keeps the
     // divergent insert path off the scan.
-    auto knn_chunk = [&]() {
+    auto knn_body = [&](auto q_first) {
+        constexpr int Q0 = decltype(q_first)::value;
         unsigned mask[Q];
         #pragma unroll
         for (int q = 0; q < Q; q++) mask[q] = 0u;
-        #pragma unroll
+        #pragma unroll 8
         for (int j = 0; j < 32; j++) {
             double cc[D];
             #pragma unroll
             for (int d = 0; d < D; d++) cc[d] = buf[d][j];
+            const unsigned bit = 1u << j;
             #pragma unroll
-            for (int q = 0; q < Q; q++) {
+            for (int q = Q0; q < Q; q++) {
                 bool l = true;
                 #pragma unroll
                 for (int d = 0; d < D; d++) l = l & (fabs(qc[q][d] - cc[d]) < L[q][KCAP - 1]);
-                asm("{.reg .pred p; setp.ne.b32 p, %1, 0; @p or.b32 %0, %0, %2;}" : "+r"(mask[q]) : "r"((int)l), "r"(1u << j));
+                asm("{.reg .pred p; setp.ne.b32 p, %1, 0; @p or.b32 %0, %0, %2;}" : "+r"(mask[q]) : "r"((int)l), "r"(bit));
             }
         }
         #pragma unroll
-        for (int q = 0; q < Q; q++) {
+        for (int q = Q0; q < Q; q++) {
             while (mask[q]) {
                 const int j = __ffs(mask[q]) - 1;
                 mask[q] &= mask[q] - 1;
@@ -443,10 +443,69 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             }
         }
     };
-    const unsigned long long nvis = sweep(
-        [&](double znext) { bool f = false;
+    auto knn_chunk = [&](bool all) {
+        if (all) knn_body(std::integral_constant<int, 0>{}); else knn_body(std::integral_constant<int, Q - 1>{});
+    };
+
+    unsigned long long nvis = centre(knn_chunk);
+
+    // Regroup the warp's 32*Q queries by local sparsity: key = k-th distance among the warp's own points (a close proxy of
+    // eps: it orders the queries almost as the final eps does).  Slot q receives the queries of rank [32q, 32q+32), so
+    // the lanes of a slot stop needing far chunks at about the same time.  Every per-query value moves with its query.
+    if (Q > 1) {
+        double* kb = &buf[0][0];                                   // >= 32*Q doubles (D + WEIGHTED >= Q)
+        double key[Q]; int pos[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) key[q] = qok[q] ? L[q][KCAP - 1] : INFINITY;
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) kb[q * 32 + lane] = key[q];
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) pos[q] = 0;
+        for (int j = 0; j < 32 * Q; j++) {
+            const double kj = kb[j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) pos[q] += ((kj < key[q]) | ((kj == key[q]) & (j < q * 32 + lane))) ? 1 : 0;
+        }
+        auto move = [&](double (&v)[Q]) {
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) kb[pos[q]] = v[q];
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = kb[q * 32 + lane];
+        };
+        double t[Q];
+        #pragma unroll
+        for (int d = 0; d < D; d++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) t[q] = qc[q][d];
+            move(t);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) qc[q][d] = t[q];
+        }
+        #pragma unroll
+        for (int e = 0; e < KCAP; e++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) t[q] = L[q][e];
+            move(t);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) L[q][e] = t[q];
+        }
+        if (WEIGHTED) move(qw);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) t[q] = (double)(2 * (int64_t)qidx[q] + (qok[q] ? 1 : 0));     // exact: < 2^32
+        move(t);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { const int64_t c = (int64_t)t[q]; qidx[q] = (int)(c >> 1); qok[q] = (c & 1) != 0; }
+        __syncwarp();
+    }
+
+    nvis += sweep(
+        [&](double znext) { unsigned f = 0u;
                             #pragma unroll
-                            for (int q = 0; q < Q; q++) f = f | (fabs(qc[q][KEY] - znext) < L[q][KCAP - 1]);
+                            for (int q = 0; q < Q; q++) f |= (fabs(qc[q][KEY] - znext) < L[q][KCAP - 1]) ? (1u << q) : 0u;
                             return f; },
         knn_chunk);
 
@@ -460,7 +519,8 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
     #pragma unroll
     for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
 
-    auto count_chunk = [&]() {
+    auto count_body = [&](auto q_first) {
+        constexpr int Q0 = decltype(q_first)::value;
         #pragma unroll 4
         for (int j = 0; j < 32; j++) {
             double cc[D];
@@ -469,7 +529,7 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             double wj_ = 0.0;
             if (WEIGHTED) wj_ = buf[D][j];
             #pragma unroll
-            for (int q = 0; q < Q; q++) {
+            for (int q = Q0; q < Q; q++) {
                 bool pz = true, px = true, py = true;
                 #pragma unroll
                 for (int d = 0; d < DZ; d++) pz = pz & (fabs(qc[q][DX + DY + d] - cc[DX + DY + d]) <= eps[q]);
@@ -483,10 +543,14 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             }
         }
     };
-    const unsigned long long nvis2 = sweep(
-        [&](double znext) { bool f = false;
+    auto count_chunk = [&](bool all) {
+        if (all) count_body(std::integral_constant<int, 0>{}); else count_body(std::integral_constant<int, Q - 1>{});
+    };
+    unsigned long long nvis2 = centre(count_chunk);
+    nvis2 += sweep(
+        [&](double znext) { unsigned f = 0u;
                             #pragma unroll
-                            for (int q = 0; q < Q; q++) f = f | (fabs(qc[q][KEY] - znext) <= eps[q]);
+                            for (int q = 0; q < Q; q++) f |= (fabs(qc[q][KEY] - znext) <= eps[q]) ? (1u << q) : 0u;
                             return f; },
         count_chunk);
 
@@ -515,7 +579,7 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if (lane == 0) {
         partial[(size_t)job * warps_per_job + wj] = acc;
-        if (visited) { atomicAdd(visited, nvis * 32ull * 32ull * Q); atomicAdd(visited + 1, nvis2 * 32ull * 32ull * Q); }
+        if (visited) { atomicAdd(visited, nvis * 32ull * 32ull); atomicAdd(visited + 1, nvis2 * 32ull * 32ull); }
     }
 }
 

@@ -107,13 +107,18 @@ def rdi_synthetic(G, T, seed):
 class FakeAnnData:
     """Duck-typed AnnData: var_names / obs_names (pandas Index), layers (cells x genes), uns, [:, genes]."""
 
-    def __init__(self, layers, var_names, obs_names=None, uns=None):
+    def __init__(self, layers, var_names, obs_names=None, uns=None, X=None, obs=None):
         import pandas as pd
+        self.X = X
+        self.obs = obs
         self.var_names = pd.Index(var_names)
-        n = next(iter(layers.values())).shape[0]
+        n = next(iter(layers.values())).shape[0] if layers else X.shape[0]
         self.obs_names = pd.Index(obs_names if obs_names is not None else ["c%d" % i for i in range(n)])
         self.layers = layers
         self.uns = {} if uns is None else uns
+
+    def obs_keys(self):
+        return [] if self.obs is None else list(self.obs.columns)
 
     def __getitem__(self, key):
         _, genes = key

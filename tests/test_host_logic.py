@@ -133,3 +133,37 @@ def test_two_rank_gloo_sharding(golden):
         assert calls == [12]                              # 24 jobs (12 ordered pairs x 2 delays) split evenly
         assert np.allclose(r1, golden["d_rdi_1"], atol=1e-12, rtol=0, equal_nan=True)
         assert np.allclose(r2, golden["d_rdi_2"], atol=1e-12, rtol=0, equal_nan=True)
+
+
+def test_load_anndata_branches_as_runs(S):
+    """branches become runs ordered by pseudotime; rdi on the loaded model == oracle on that ordering"""
+    from oracle import ksg_oracle as o
+    rng = np.random.default_rng(8)
+    G, n = 4, 90
+    X = rng.standard_normal((n, G)).cumsum(axis=0) * 0.3 + rng.standard_normal((n, G))
+    branch = np.array(["1"] * 50 + ["2"] * 39 + ["3"])                    # branch "3" has one cell -> dropped
+    perm = rng.permutation(n)
+    X, branch = X[perm], branch[perm]
+    ptime = rng.random(n)
+    obs = pd.DataFrame({"dpt_groups": branch, "dpt_pseudotime": ptime}, index=["c%d" % i for i in range(n)])
+    genes = ["A", "B", "C", "D"]
+    ad = recipes.FakeAnnData({"spliced": X.copy()}, genes, obs_names=list(obs.index), X=X, obs=obs)
+    m = S.load_anndata(ad)
+    assert list(m.node_ids) == genes and list(m.run_ids) == ["1", "2"]
+    assert m.expression.shape == (8, 50) and m.spliced.shape == (n, G) and m.velocity is None
+    ids, E, ro = m._dense()
+    assert list(ro) == [0, 50, 89]
+    runs = []
+    for key in ("1", "2"):
+        c = np.where(branch == key)[0]; c = c[np.argsort(ptime[c], kind="stable")]
+        runs.append(X[c].T)
+    assert np.array_equal(E, np.concatenate(runs, axis=1))
+    r = m.rdi([1, 2])
+    ref = o.rdi([[run[g] for run in runs] for g in range(G)], [1, 2])
+    for d in (1, 2):
+        assert np.allclose(r[d].to_numpy(dtype=float), ref[d], atol=1e-12, rtol=0, equal_nan=True)
+    # no branch annotation -> one run in the given cell order
+    ad2 = recipes.FakeAnnData({}, genes, obs_names=list(obs.index), X=X, obs=pd.DataFrame(index=obs.index))
+    m2 = S.load_anndata(ad2)
+    assert m2.expression.shape == (G, n) and list(m2.run_ids) == [0]
+    assert np.array_equal(m2._dense()[1], X.T)
