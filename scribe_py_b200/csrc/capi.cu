@@ -294,8 +294,8 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
             CU(cudaMemcpyAsync(h->dims.p, pd.data(), sizeof(int) * dp, cudaMemcpyHostToDevice, h->stream));
             const double scale = std::sqrt(1.4426950408889634 / (2.0 * o->bw * o->bw));
             if (ks) {
-                const int bps = (wpj + TPB / 32 - 1) / (TPB / 32);
-                ks<<<(unsigned)(nj * bps), TPB, 0, h->stream>>>(dj, wpj, h->dims.as<int>(), scale, u, visited);
+                const int bps = (wpj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
+                ks<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, wpj, h->dims.as<int>(), scale, u, visited);
             } else {
                 kf<<<(unsigned)(nj * bpj_kde), TPB, 0, h->stream>>>(dj, bpj_kde, h->dims.as<int>(), scale, u);
             }
@@ -332,8 +332,8 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     if (sweep) {
         h->partial.ensure(sizeof(double) * nj * wpj);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * wpj, h->stream));
-        const int bps = (wpj + TPB / 32 - 1) / (TPB / 32);
-        sweep<<<(unsigned)(nj * bps), TPB, 0, h->stream>>>(dj, wpj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
+        const int bps = (wpj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
+        sweep<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, wpj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
         CU(cudaGetLastError());
         finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), wpj, (int)nj, out_dev);
         CU(cudaGetLastError());

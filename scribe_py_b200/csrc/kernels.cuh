@@ -303,8 +303,13 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
 // an exact superset of what the dense kernel would have accepted: results are bit-identical to it.
 // No block-level synchronisation: warps are independent (chunks are staged in a per-warp shared-memory buffer).
 // ------------------------------------------------------------------------------------------------
+// Sweep kernels: warps are independent and their windows differ in size, so CTAs are kept small (SWEEP_TPB threads)
+// to let a finished warp's slot be refilled early; SWEEP_MIN_CTAS caps registers for 24 resident warps per SM.
+#ifndef SWEEP_TPB
+#define SWEEP_TPB 64
+#endif
 #ifndef SWEEP_MIN_CTAS
-#define SWEEP_MIN_CTAS 3
+#define SWEEP_MIN_CTAS (768 / SWEEP_TPB)
 #endif
 template <int D, bool WEIGHTED>
 struct Chunk { double v[D]; double w; };
@@ -323,13 +328,13 @@ __device__ __forceinline__ Chunk<D, WEIGHTED> load_chunk(const JobDesc& jd, int 
 }
 
 template <int DX, int DY, int DZ, int KCAP, int Q, bool WEIGHTED>
-__global__ void __launch_bounds__(TPB, SWEEP_MIN_CTAS)
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
 ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                  double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
     constexpr int D = DX + DY + DZ;
     constexpr int KEY = D - 1;
-    constexpr int W = TPB / 32;
+    constexpr int W = SWEEP_TPB / 32;
     __shared__ __align__(16) double sbuf[W][D + (WEIGHTED ? 1 : 0)][32];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -589,11 +594,11 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
 constexpr double KDE_CUT = 64.0;
 
 template <int DP, int Q>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(SWEEP_TPB)
 kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int* __restrict__ dims, double scale,
                  double* __restrict__ u_out, unsigned long long* __restrict__ visited)
 {
-    constexpr int W = TPB / 32;
+    constexpr int W = SWEEP_TPB / 32;
     constexpr int KEY = DP - 1;                                   // dims[] lists the key column last
     __shared__ __align__(16) double sbuf[W][DP][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
