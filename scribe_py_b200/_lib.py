@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libscribe_b200.so")
+LIB_PATH = os.environ.get("SCRIBE_B200_LIB") or os.path.join(_HERE, "lib", "libscribe_b200.so")   # override: tuning builds
 
 SCRIBE_OK, E_ARG, E_LENGTH, E_CUDA, E_DOMAIN, E_STATE = 0, 1, 2, 3, 4, 5
 EST_MI, EST_CMI, EST_UMI, EST_CUMI = 0, 1, 2, 3

@@ -113,6 +113,56 @@ __device__ __forceinline__ void add_if(double& acc, double v, bool p) {
     asm("{.reg .pred q; setp.ne.b32 q, %2, 0; @q add.f64 %0, %0, %1;}" : "+d"(acc) : "d"(v), "r"((int)p));
 }
 
+// One (query, candidate) step of the count pass as a single PTX block: the predicates live only inside the block, so the
+// compiler cannot spill them to registers when several queries and unrolled candidates are in flight (7 predicate
+// registers per thread).  dq* are the coordinate differences q - c; semantics as in the reference's four ball tests
+// (information_estimators.py:169-172): nz += [|dz|<=e], nxz += [|dx|<=e & z], nyz += [|dy|<=e & z], nxyz += [all].
+template <int DZ, bool WEIGHTED>
+__device__ __forceinline__ void count_step(double dx, double dy, const double (&dz)[DZ > 0 ? DZ : 1], double e, double wj,
+                                           int& nz, int& nxz, int& nyz, int& nxyz, double& wz, double& wyz)
+{
+    static_assert(DZ >= 1 && DZ <= 3, "count_step supports 1..3 conditioning dimensions");
+    if (DZ == 1) {
+        if (WEIGHTED)
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az;\n abs.f64 ax,%6; abs.f64 ay,%7; abs.f64 az,%8;\n"
+                " setp.le.f64 pz, az, %9;\n setp.le.and.f64 pxz, ax, %9, pz;\n setp.le.and.f64 pyz, ay, %9, pz;\n setp.le.and.f64 pxyz, ay, %9, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n"
+                " @pz add.f64 %4,%4,%10;\n @pyz add.f64 %5,%5,%10;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz), "+d"(wz), "+d"(wyz) : "d"(dx), "d"(dy), "d"(dz[0]), "d"(e), "d"(wj));
+        else
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az;\n abs.f64 ax,%4; abs.f64 ay,%5; abs.f64 az,%6;\n"
+                " setp.le.f64 pz, az, %7;\n setp.le.and.f64 pxz, ax, %7, pz;\n setp.le.and.f64 pyz, ay, %7, pz;\n setp.le.and.f64 pxyz, ay, %7, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz) : "d"(dx), "d"(dy), "d"(dz[0]), "d"(e));
+    } else if (DZ == 2) {
+        if (WEIGHTED)
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az,aw;\n abs.f64 ax,%6; abs.f64 ay,%7; abs.f64 az,%8; abs.f64 aw,%9;\n"
+                " setp.le.f64 pz, az, %10;\n setp.le.and.f64 pz, aw, %10, pz;\n setp.le.and.f64 pxz, ax, %10, pz;\n setp.le.and.f64 pyz, ay, %10, pz;\n setp.le.and.f64 pxyz, ay, %10, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n"
+                " @pz add.f64 %4,%4,%11;\n @pyz add.f64 %5,%5,%11;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz), "+d"(wz), "+d"(wyz) : "d"(dx), "d"(dy), "d"(dz[0]), "d"(dz[DZ > 1 ? 1 : 0]), "d"(e), "d"(wj));
+        else
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az,aw;\n abs.f64 ax,%4; abs.f64 ay,%5; abs.f64 az,%6; abs.f64 aw,%7;\n"
+                " setp.le.f64 pz, az, %8;\n setp.le.and.f64 pz, aw, %8, pz;\n setp.le.and.f64 pxz, ax, %8, pz;\n setp.le.and.f64 pyz, ay, %8, pz;\n setp.le.and.f64 pxyz, ay, %8, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz) : "d"(dx), "d"(dy), "d"(dz[0]), "d"(dz[DZ > 1 ? 1 : 0]), "d"(e));
+    } else {
+        if (WEIGHTED)
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az,aw,av;\n abs.f64 ax,%6; abs.f64 ay,%7; abs.f64 az,%8; abs.f64 aw,%9; abs.f64 av,%10;\n"
+                " setp.le.f64 pz, az, %11;\n setp.le.and.f64 pz, aw, %11, pz;\n setp.le.and.f64 pz, av, %11, pz;\n setp.le.and.f64 pxz, ax, %11, pz;\n setp.le.and.f64 pyz, ay, %11, pz;\n setp.le.and.f64 pxyz, ay, %11, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n"
+                " @pz add.f64 %4,%4,%12;\n @pyz add.f64 %5,%5,%12;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz), "+d"(wz), "+d"(wyz)
+                : "d"(dx), "d"(dy), "d"(dz[0]), "d"(dz[DZ > 1 ? 1 : 0]), "d"(dz[DZ > 2 ? 2 : 0]), "d"(e), "d"(wj));
+        else
+            asm("{\n .reg .pred pz,pxz,pyz,pxyz;\n .reg .f64 ax,ay,az,aw,av;\n abs.f64 ax,%4; abs.f64 ay,%5; abs.f64 az,%6; abs.f64 aw,%7; abs.f64 av,%8;\n"
+                " setp.le.f64 pz, az, %9;\n setp.le.and.f64 pz, aw, %9, pz;\n setp.le.and.f64 pz, av, %9, pz;\n setp.le.and.f64 pxz, ax, %9, pz;\n setp.le.and.f64 pyz, ay, %9, pz;\n setp.le.and.f64 pxyz, ay, %9, pxz;\n"
+                " @pz add.s32 %0,%0,1;\n @pxz add.s32 %1,%1,1;\n @pyz add.s32 %2,%2,1;\n @pxyz add.s32 %3,%3,1;\n}"
+                : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz)
+                : "d"(dx), "d"(dy), "d"(dz[0]), "d"(dz[DZ > 1 ? 1 : 0]), "d"(dz[DZ > 2 ? 2 : 0]), "d"(e));
+    }
+}
+
 // Shared-memory tile of candidates: D rows of `cap` doubles (+ one row of weights), dynamic size.
 // cap = min(round_up(n_max, 4), FUSED_TILE_MAX): jobs up to FUSED_TILE_MAX points are staged ONCE for both passes.
 constexpr int FUSED_TILE_MAX = 2048;
@@ -332,6 +382,7 @@ __global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
 ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                  double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
+    static_assert(DX == 1 && DY == 1 && DZ >= 1, "sweep kernels: scalar x and y, at least one conditioning column");
     constexpr int D = DX + DY + DZ;
     constexpr int KEY = D - 1;
     constexpr int W = SWEEP_TPB / 32;
@@ -443,7 +494,7 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
                 mask[q] &= mask[q] - 1;
                 double dd = fabs(qc[q][0] - buf[0][j]);
                 #pragma unroll
-                for (int d = 1; d < D; d++) dd = fmax(dd, fabs(qc[q][d] - buf[d][j]));
+                for (int d = 1; d < D; d++) { const double a = fabs(qc[q][d] - buf[d][j]); dd = (a > dd) ? a : dd; }   // no NaNs here
                 if (dd < L[q][KCAP - 1]) topk_insert<KCAP>(L[q], dd);          // the bar may have moved since the scan
             }
         }
@@ -535,16 +586,11 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             if (WEIGHTED) wj_ = buf[D][j];
             #pragma unroll
             for (int q = Q0; q < Q; q++) {
-                bool pz = true, px = true, py = true;
+                double dzv[DZ];
                 #pragma unroll
-                for (int d = 0; d < DZ; d++) pz = pz & (fabs(qc[q][DX + DY + d] - cc[DX + DY + d]) <= eps[q]);
-                #pragma unroll
-                for (int d = 0; d < DX; d++) px = px & (fabs(qc[q][d] - cc[d]) <= eps[q]);
-                #pragma unroll
-                for (int d = 0; d < DY; d++) py = py & (fabs(qc[q][DX + d] - cc[DX + d]) <= eps[q]);
-                const bool pxz = px & pz, pyz = py & pz, pxyz = pxz & py;
-                inc_if(nz[q], pz); inc_if(nxz[q], pxz); inc_if(nyz[q], pyz); inc_if(nxyz[q], pxyz);
-                if (WEIGHTED) { add_if(wz[q], wj_, pz); add_if(wyz[q], wj_, pyz); }
+                for (int d = 0; d < DZ; d++) dzv[d] = qc[q][DX + DY + d] - cc[DX + DY + d];
+                count_step<DZ, WEIGHTED>(qc[q][0] - cc[0], qc[q][DX] - cc[DX], dzv, eps[q], wj_,
+                                         nz[q], nxz[q], nyz[q], nxyz[q], wz[q], wyz[q]);
             }
         }
     };
