@@ -490,6 +490,9 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         const int dz = L + 1, D = dz + 2;
         // chunk: same n_cond, bounded workspace
         std::unordered_map<ColKey, int, ColKeyHash> colmap;
+        colmap.reserve(8192);
+        ColKey last_key[2 + SCRIBE_MAX_COND + 1]; int last_id[2 + SCRIBE_MAX_COND + 1];     // per-role one-entry cache: jobs arrive
+        for (auto& v : last_id) v = -1;                                                      // target-major, so y/z columns repeat
         std::vector<ColSpec> specs;
         std::vector<JobDesc> hj;
         std::vector<int> colidx;          // D per job
@@ -515,21 +518,26 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             if (end > pos && ws > h->ws_budget) break;
             n_max = (int)new_nmax;
             const double sx = scales ? scales[3 * end] : 1.0, sy = scales ? scales[3 * end + 1] : 1.0, sz = scales ? scales[3 * end + 2] : 1.0;
-            auto get = [&](int gene, int shift, int diff, double sc) {
+            auto get = [&](int role, int gene, int shift, int diff, double sc) {
                 ColKey key{gene, shift, tau, diff, 0};
                 std::memcpy(&key.scale_bits, &sc, 8);
+                if (last_id[role] >= 0 && last_key[role] == key) return last_id[role];
+                int id;
                 auto it = colmap.find(key);
-                if (it != colmap.end()) return it->second;
-                const int id = (int)specs.size();
-                specs.push_back(ColSpec{gene, shift, tau, diff, sc});
-                colmap.emplace(key, id);
+                if (it != colmap.end()) id = it->second;
+                else {
+                    id = (int)specs.size();
+                    specs.push_back(ColSpec{gene, shift, tau, diff, sc});
+                    colmap.emplace(key, id);
+                }
+                last_key[role] = key; last_id[role] = id;
                 return id;
             };
-            colidx.push_back(get(jb.src, tau - jb.delay, 0, sx));                    // x   (cn:147,:266)
-            colidx.push_back(get(jb.dst, tau, differential ? 1 : 0, sy));            // y   (cn:151-153,:269-271)
+            colidx.push_back(get(0, jb.src, tau - jb.delay, 0, sx));                 // x   (cn:147,:266)
+            colidx.push_back(get(1, jb.dst, tau, differential ? 1 : 0, sy));         // y   (cn:151-153,:269-271)
             for (int c = L - 1; c >= 0; c--)                                         // z: cond[L-1] .. cond[0], then dst's past (cn:273-278)
-                colidx.push_back(get(jb.cond_gene[c], tau - jb.cond_delay[c], 0, sz));
-            colidx.push_back(get(jb.dst, tau - 1, 0, sz));                           //     (cn:149,:267)
+                colidx.push_back(get(2 + c, jb.cond_gene[c], tau - jb.cond_delay[c], 0, sz));
+            colidx.push_back(get(2 + SCRIBE_MAX_COND, jb.dst, tau - 1, 0, sz));      //     (cn:149,:267)
             JobDesc jd; std::memset(&jd, 0, sizeof(jd)); jd.n = (int)n;
             hj.push_back(jd);
             h->st.point_pairs += n * n;
@@ -565,9 +573,15 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             const int nk = (int)keyspec.size();
             h->keys_in.ensure(sizeof(double) * nk * stride);
             h->perm.ensure(sizeof(int32_t) * nk * stride);
-            for (int i = 0; i < nk; i++)       // device-to-device copies of the key columns into one contiguous block
-                CU(cudaMemcpyAsync(h->keys_in.as<double>() + (size_t)i * stride, h->cols.as<double>() + (size_t)keyspec[i] * stride,
-                                   sizeof(double) * keylen[i], cudaMemcpyDeviceToDevice, h->stream));
+            h->keyspecs.ensure(sizeof(int) * nk);
+            CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
+            for (int k0 = 0; k0 < nk; k0 += 65535) {      // key columns -> one contiguous block (gridDim.y limit)
+                dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min(65535, nk - k0));
+                select_columns_kernel<<<grid, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
+                                                                   h->keys_in.as<double>() + (size_t)k0 * stride);
+                CU(cudaGetLastError());
+                h->st.kernel_launches++;
+            }
             sort_segments(h, h->keys_in.as<double>(), nk, stride, keylen, h->perm.as<int32_t>());
             for (int64_t j = 0; j < nj; j++) hj[j].perm = h->perm.as<int32_t>() + (size_t)slot[colidx[j * D + D - 1]] * stride;
             ordered = true;

@@ -748,6 +748,15 @@ kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int*
     if (lane == 0 && visited) atomicAdd(visited + 2, nvis * 32ull * 32ull * Q);
 }
 
+// copy selected columns of a [n_cols][stride] block into a contiguous [n_sel][stride] block (sort keys)
+__global__ void __launch_bounds__(TPB)
+select_columns_kernel(const double* __restrict__ cols, const int* __restrict__ sel, int64_t stride, double* __restrict__ out)
+{
+    const double* src = cols + (size_t)sel[blockIdx.y] * stride;
+    double* dst = out + (size_t)blockIdx.y * stride;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < stride; i += (int64_t)gridDim.x * TPB) dst[i] = src[i];
+}
+
 __global__ void iota_segments_kernel(int32_t* __restrict__ v, int64_t stride, int n_seg) {
     const int64_t total = stride * n_seg;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
