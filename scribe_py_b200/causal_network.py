@@ -121,10 +121,15 @@ class causal_model(object):
         blocks, lengths = [], []
         for run in runs:
             if run is None:
-                vals = expr.loc[node_ids].to_numpy(dtype=np.float64)
+                aligned = len(expr.index) == len(node_ids) and list(expr.index) == node_ids
+                vals = (expr if aligned else expr.loc[node_ids]).to_numpy(dtype=np.float64)
             else:
                 vals = expr.loc[[(g, run) for g in node_ids]].to_numpy(dtype=np.float64)
-            ok = ~np.isnan(vals)
+            bad = np.isnan(vals)
+            if not bad.any():                                    # common case: no padding at all
+                blocks.append(vals); lengths.append(vals.shape[1])
+                continue
+            ok = ~bad
             cnt = ok.sum(axis=1)
             assert (cnt == cnt[0]).all(), "Lists should have same length"
             T = int(cnt[0])
@@ -136,7 +141,7 @@ class causal_model(object):
                 blk = np.stack([vals[g][ok[g]] for g in range(len(node_ids))])
             blocks.append(blk)
             lengths.append(T)
-        E = np.ascontiguousarray(np.concatenate(blocks, axis=1))
+        E = np.ascontiguousarray(blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1))
         run_off = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
         return node_ids, E, run_off
 
@@ -162,7 +167,11 @@ class causal_model(object):
         return out
 
     def _frame(self, M, node_ids):
-        return pd.DataFrame(M, index=node_ids, columns=node_ids)
+        ix = getattr(self, "_ix_cache", None)
+        if ix is None or len(ix[0]) != len(node_ids) or ix[0] != node_ids:      # build the label Index once per gene list
+            ix = (list(node_ids), pd.Index(node_ids))
+            self._ix_cache = ix
+        return pd.DataFrame(M, index=ix[1], columns=ix[1], copy=False)
 
     def _rdi_plan(self, delays, differential_mode=False):
         """Host-side job table of one rdi() call: every ordered pair x delay, ordered delay-major, then
@@ -273,6 +282,13 @@ class causal_model(object):
         return self.crdi_results
 
     # ------------------------------------------------------------------ reductions over the RDI matrices
+    @staticmethod
+    def __square(frame, node_ids, dtype=np.float64):
+        """frame.loc[node_ids, node_ids] as an array, without the label lookup when the frame is already in node order."""
+        if frame.shape == (len(node_ids), len(node_ids)) and list(frame.index) == node_ids and list(frame.columns) == node_ids:
+            return frame.to_numpy(dtype=dtype)
+        return frame.loc[node_ids, node_ids].to_numpy(dtype=dtype)
+
     def __extract_max_rdi_value_delay(self):
         """Max over delays and the delay attaining it; strict '>' so the first delay wins ties, the diagonal
         keeps -inf / NaN (causal_network.py:295-311, without the removed np.int)."""
@@ -283,7 +299,7 @@ class causal_model(object):
         for delay, frame in self.rdi_results.items():
             if isinstance(delay, str) and delay == "MAX":
                 continue
-            M = frame.loc[node_ids, node_ids].to_numpy(dtype=np.float64)
+            M = self.__square(frame, node_ids)
             better = M > val
             np.fill_diagonal(better, False)
             val[better] = M[better]
@@ -294,8 +310,8 @@ class causal_model(object):
         """Per target the k_nodes+1 strongest sources by streaming replace-first-minimum
         (causal_network.py:316-333)."""
         node_ids = list(self.node_ids)
-        V = max_rdi_values.loc[node_ids, node_ids].to_numpy(dtype=np.float64)
-        Dl = max_rdi_delays.loc[node_ids, node_ids].to_numpy()
+        V = self.__square(max_rdi_values, node_ids)
+        Dl = self.__square(max_rdi_delays, node_ids, dtype=object)
         top_nodes, top_delays, top_values = {}, {}, {}
         for b_i, b in enumerate(node_ids):
             nodes = [None] * (k_nodes + 1); dls = [np.nan] * (k_nodes + 1); vals = [-np.inf] * (k_nodes + 1)
