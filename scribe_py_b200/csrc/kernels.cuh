@@ -94,15 +94,16 @@ __device__ __forceinline__ double block_sum(double v, double* smem8) {
 // ------------------------------------------------------------------------------------------------
 template <int KCAP>
 __device__ __forceinline__ void topk_insert(double (&L)[KCAP], double d) {
-    // L ascending; caller guarantees d < L[KCAP-1]
-    L[KCAP - 1] = d;
+    // L ascending; caller guarantees d < L[KCAP-1].  All position tests are independent of one another and every new
+    // slot depends only on old slots, so the dependency depth is 2 instead of the 2*(KCAP-1) of a compare-swap chain
+    // (the insert path is latency-bound: few lanes are active and the FP64 compare is ~10 cycles).
+    bool p[KCAP];
     #pragma unroll
-    for (int t = KCAP - 1; t > 0; --t) {
-        const double a = L[t - 1], b = L[t];
-        const bool s = b < a;
-        L[t - 1] = s ? b : a;
-        L[t]     = s ? a : b;
-    }
+    for (int t = 0; t < KCAP - 1; t++) p[t] = d < L[t];
+    p[KCAP - 1] = true;
+    #pragma unroll
+    for (int t = KCAP - 1; t > 0; --t) L[t] = p[t - 1] ? L[t - 1] : (p[t] ? d : L[t]);
+    L[0] = p[0] ? d : L[0];
 }
 
 // predicated accumulators: one issue slot each (the compiler otherwise emits add + select pairs)
@@ -161,6 +162,27 @@ __device__ __forceinline__ void count_step(double dx, double dy, const double (&
                 : "+r"(nz), "+r"(nxz), "+r"(nyz), "+r"(nxyz)
                 : "d"(dx), "d"(dy), "d"(dz[0]), "d"(dz[DZ > 1 ? 1 : 0]), "d"(dz[DZ > 2 ? 2 : 0]), "d"(e));
     }
+}
+
+// One (query, candidate) step of the kNN scan as a single PTX block: sets `bit` in `mask` when every coordinate
+// difference is strictly below the query's current k-th distance `thr` (strict, like the insert test).
+template <int D>
+__device__ __forceinline__ void knn_mark(const double (&df)[D], double thr, unsigned bit, unsigned& mask)
+{
+    static_assert(D >= 3 && D <= 5, "knn_mark supports joint dimension 3..5");
+    if (D == 3)
+        asm("{\n .reg .pred p;\n .reg .f64 a0,a1,a2;\n abs.f64 a0,%1; abs.f64 a1,%2; abs.f64 a2,%3;\n"
+            " setp.lt.f64 p, a0, %4;\n setp.lt.and.f64 p, a1, %4, p;\n setp.lt.and.f64 p, a2, %4, p;\n @p or.b32 %0,%0,%5;\n}"
+            : "+r"(mask) : "d"(df[0]), "d"(df[1]), "d"(df[2]), "d"(thr), "r"(bit));
+    else if (D == 4)
+        asm("{\n .reg .pred p;\n .reg .f64 a0,a1,a2,a3;\n abs.f64 a0,%1; abs.f64 a1,%2; abs.f64 a2,%3; abs.f64 a3,%4;\n"
+            " setp.lt.f64 p, a0, %5;\n setp.lt.and.f64 p, a1, %5, p;\n setp.lt.and.f64 p, a2, %5, p;\n setp.lt.and.f64 p, a3, %5, p;\n @p or.b32 %0,%0,%6;\n}"
+            : "+r"(mask) : "d"(df[0]), "d"(df[1]), "d"(df[2]), "d"(df[D > 3 ? 3 : 0]), "d"(thr), "r"(bit));
+    else
+        asm("{\n .reg .pred p;\n .reg .f64 a0,a1,a2,a3,a4;\n abs.f64 a0,%1; abs.f64 a1,%2; abs.f64 a2,%3; abs.f64 a3,%4; abs.f64 a4,%5;\n"
+            " setp.lt.f64 p, a0, %6;\n setp.lt.and.f64 p, a1, %6, p;\n setp.lt.and.f64 p, a2, %6, p;\n setp.lt.and.f64 p, a3, %6, p;\n setp.lt.and.f64 p, a4, %6, p;\n"
+            " @p or.b32 %0,%0,%7;\n}"
+            : "+r"(mask) : "d"(df[0]), "d"(df[1]), "d"(df[2]), "d"(df[D > 3 ? 3 : 0]), "d"(df[D > 4 ? 4 : 0]), "d"(thr), "r"(bit));
 }
 
 // Shared-memory tile of candidates: D rows of `cap` doubles (+ one row of weights), dynamic size.
@@ -481,10 +503,10 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
             const unsigned bit = 1u << j;
             #pragma unroll
             for (int q = Q0; q < Q; q++) {
-                bool l = true;
+                double df[D];
                 #pragma unroll
-                for (int d = 0; d < D; d++) l = l & (fabs(qc[q][d] - cc[d]) < L[q][KCAP - 1]);
-                asm("{.reg .pred p; setp.ne.b32 p, %1, 0; @p or.b32 %0, %0, %2;}" : "+r"(mask[q]) : "r"((int)l), "r"(bit));
+                for (int d = 0; d < D; d++) df[d] = qc[q][d] - cc[d];
+                knn_mark<D>(df, L[q][KCAP - 1], bit, mask[q]);
             }
         }
         #pragma unroll

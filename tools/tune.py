@@ -41,3 +41,8 @@ if __name__ == "__main__":
     elif what == "cumi":
         run(40, 2000, [1, 5, 10], _lib.EST_CUMI)
         run(16, 20000, [1], _lib.EST_CUMI)
+    elif what == "c5":
+        run(16, 20000, [1], _lib.EST_CMI)
+        run(16, 20000, [1], _lib.EST_CUMI)
+        run(30, 5000, [1], _lib.EST_CMI)
+        run(30, 5000, [1], _lib.EST_CUMI)
