@@ -223,3 +223,43 @@ def test_full_size_properties(S):
         dist = np.abs(P - P[i]).max(axis=1)
         assert d["eps"][i] == np.sort(dist)[5]
         assert c[3][i] == (np.abs(P[:, 2] - P[i, 2]) <= d["eps"][i]).sum() - 1
+
+
+def test_load_anndata_rdi_on_gpu(S):
+    """AnnData -> causal_model (branches as runs, pseudotime order) -> rdi on the GPU == oracle on the same ordering"""
+    rng = np.random.default_rng(8)
+    G, n = 4, 300
+    X = rng.standard_normal((n, G)).cumsum(axis=0) * 0.3 + rng.standard_normal((n, G))
+    branch = np.array(["1"] * 170 + ["2"] * 130)
+    perm = rng.permutation(n)
+    X, branch = X[perm], branch[perm]
+    ptime = rng.random(n)
+    obs = pd.DataFrame({"dpt_groups": branch, "dpt_pseudotime": ptime}, index=["c%d" % i for i in range(n)])
+    ad = recipes.FakeAnnData({}, ["A", "B", "C", "D"], obs_names=list(obs.index), X=X, obs=obs)
+    m = S.load_anndata(ad)
+    r = m.rdi([1, 3])
+    runs = []
+    for key in ("1", "2"):
+        c = np.where(branch == key)[0]; c = c[np.argsort(ptime[c], kind="stable")]
+        runs.append(X[c].T)
+    ref = o.rdi([[run[g] for run in runs] for g in range(G)], [1, 3])
+    for d in (1, 3):
+        assert np.allclose(r[d].to_numpy(dtype=float), ref[d], atol=TOL_EXACT, rtol=0, equal_nan=True)
+
+
+def test_stats_and_paths(S):
+    """per-pass visit counters: the dense kernels visit N^2 pairs per pass, the sweep strictly fewer, same answer"""
+    h = S._lib.default_handle()
+    E = recipes.rdi_synthetic(3, 1500, 4)
+    x, y, z = E[0, :-1, None], E[1, 1:, None], E[1, :-1, None]
+    n = len(x)
+    vals = {}
+    for name, path in (("dense", S._lib.PATH_DENSE), ("sweep", S._lib.PATH_SWEEP)):
+        vals[name] = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CMI, 5, path=path))
+        st = h.stats()
+        assert st["jobs"] == 1 and st["kernel_launches"] >= 2 and st["estimator_ms"] > 0
+        if name == "dense":
+            assert st["visited_knn"] == n * n and st["visited_count"] == n * n
+        else:
+            assert 0 < st["visited_knn"] < n * n and 0 < st["visited_count"] < n * n
+    assert vals["dense"] == vals["sweep"] or abs(vals["dense"] - vals["sweep"]) < 1e-13
