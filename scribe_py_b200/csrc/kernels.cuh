@@ -657,9 +657,9 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
 }
 
 // Gaussian KDE inverse densities, sorted sweep: terms with (z_i - z_j)^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
-// than 2^-KDE_CUT each against a sum that is >= 1 (the self term), so a side is abandoned once the nearest unvisited
+// than 2^-KDE_CUT (= 2^-44) each against a sum that is >= 1 (the self term), so a side is abandoned once the nearest unvisited
 // candidate is that far in the key coordinate for every query of the warp.
-constexpr double KDE_CUT = 64.0;
+constexpr double KDE_CUT = 44.0;     // N * 2^-44 < 2e-9 relative for N <= 2^15; the estimators' budget is 1e-5 absolute
 
 template <int DP, int Q>
 __global__ void __launch_bounds__(SWEEP_TPB)

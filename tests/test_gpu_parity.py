@@ -263,3 +263,45 @@ def test_stats_and_paths(S):
         else:
             assert 0 < st["visited_knn"] < n * n and 0 < st["visited_count"] < n * n
     assert vals["dense"] == vals["sweep"] or abs(vals["dense"] - vals["sweep"]) < 1e-13
+
+
+@pytest.mark.parametrize("dz", [1, 2, 3])
+@pytest.mark.parametrize("k", [3, 5, 10])
+def test_sweep_matrix_against_oracle(S, dz, k):
+    """sorted sweep across conditioning dimension and k (KCAP 6 / 16), continuous + tied key column, cmi and cumi"""
+    rng = np.random.default_rng(100 * dz + k)
+    n = 700 + 37 * dz
+    z = rng.standard_normal((n, dz))
+    z[:, -1] = np.round(z[:, -1], 1)                       # heavy ties in the sort key
+    x = 0.5 * z[:, :1] + rng.standard_normal((n, 1))
+    y = x + z[:, -1:] + 0.5 * rng.standard_normal((n, 1))
+    P = np.concatenate((x, y, z), axis=1)
+    ix, iy, iz = (0,), (1,), tuple(range(2, 2 + dz))
+    eps, cnt = o.knn_counts(P, [ix + iy + iz, ix + iz, iy + iz, iz], k)
+    for path in ("sweep", "dense"):
+        d = S.information_estimators.ksg_debug("cmi", x, y, z, k=k, path=path)
+        assert np.array_equal(d["eps"], eps), path
+        assert np.array_equal(d["counts"], cnt), path
+    h = S._lib.default_handle()
+    v_sweep = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CUMI, k, bw=0.2, path=S._lib.PATH_SWEEP))
+    v_dense = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CUMI, k, bw=0.2, path=S._lib.PATH_DENSE))
+    ref = o.cumi(x, y, z, k=k, bw=0.2)
+    assert abs(v_sweep - ref) < TOL_KDE and abs(v_dense - ref) < TOL_KDE and abs(v_sweep - v_dense) < 1e-7
+
+
+def test_sweep_zero_inflated_large(S):
+    """C3-like zero-inflated columns at N = 6000 (mask keeps ~45 %): sweep == dense == generic, per-point"""
+    rng = np.random.default_rng(12)
+    n = 6000
+    x = rng.gamma(2., 1., (n, 1)); x[rng.random((n, 1)) < 0.3] = 0
+    z = rng.gamma(2., 1., (n, 1)); z[rng.random((n, 1)) < 0.3] = 0
+    y = z + 0.1 * rng.standard_normal((n, 1)); y[rng.random((n, 1)) < 0.1] = 0
+    a = S.information_estimators.ksg_debug("cmi", x, y, z, path="dense")
+    b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
+    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    assert (a["eps"] == 0).mean() > 0.002                     # the tie case (eps = 0) is actually exercised
+    P = np.concatenate((x, y, z), axis=1)
+    for i in (0, 17, 2999, 5999):
+        dist = np.abs(P - P[i]).max(axis=1)
+        assert a["eps"][i] == np.sort(dist)[5]
+        assert a["counts"][0][i] == (dist <= a["eps"][i]).sum() - 1
