@@ -56,6 +56,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic_r1.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -291,7 +299,7 @@ def ours_arm(args):
                     "api": "scribe_py_b200.causal_model(DataFrame).rdi([1,5,10]) -> dict of DataFrames"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "alu", "achieved": achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
-                         "frac": achieved / alu_peak, "traffic": None,
+                         "frac": achieved / alu_peak, "traffic": ncu_traffic(kernel) if n_gpus == 1 else None,
                          "kernel": kernel, "kernel_ms": k_ms, "kernel_share_of_step": est_ms / dev_ms,
                          "algorithmic_ops": "6 per kNN-pass visit + 10 per count-pass visit (SURVEY 8d, D=3)",
                          "visits_per_launch": {"knn": vk, "count": vc, "dense_pairs_N2": pairs_per_launch,
