@@ -133,6 +133,12 @@ int scribe_lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs,
 int scribe_lagged_jobs_dev(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
                            int32_t differential, const double* scales, double* out_dev);
 
+/* Pairwise mutual-information network over the resident matrix: job j = mi(E[src[j]], E[dst[j]]) on all cells, no lag
+ * (other_estimators.mi, Scribe/other_estimators.py:50-83 -- dead code in the reference because its helper is shadowed,
+ * :10-11 vs :50).  opts->estimator must be SCRIBE_EST_MI. */
+int scribe_mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs,
+                   const scribe_opts* opts, double* out_host);
+
 /* ---- driver level: causal_net_dynamics_coupling (Scribe.py:110-135) --------------------------- */
 /* S, Y: n_genes rows of n_cells doubles.  S = normalised t0 layer (x and z columns, Scribe.py:119,:123);
  * Y = the y column per gene (S + V when t1_key == 'velocity', else V; Scribe.py:121). */

@@ -4,6 +4,7 @@ Module layout mirrors the reference package for the path it replaces (Scribe/__i
     information_estimators : vd, mi, cmi, umi, cumi
     causal_network         : causal_model (.rdi, .crdi, preprocessing pass-throughs)
     Scribe                 : causal_net_dynamics_coupling, CLR
+    other_estimators       : mi, corr (pairwise networks over a causal_model)
     read_export            : load_anndata (AnnData -> causal_model, branches as runs ordered by pseudotime)
 All estimator arithmetic runs in libscribe_b200.so (CUDA, FP64); there is no CPU fallback.
 """
@@ -12,11 +13,12 @@ from . import information_estimators
 from . import causal_network
 from . import Scribe
 from . import read_export
+from . import other_estimators
 from .information_estimators import vd, mi, cmi, umi, cumi
 from .causal_network import causal_model
 from .Scribe import causal_net_dynamics_coupling, CLR
 from .read_export import load_anndata
 
 __all__ = ["information_estimators", "causal_network", "Scribe", "vd", "mi", "cmi", "umi", "cumi", "causal_model",
-           "causal_net_dynamics_coupling", "CLR", "load_anndata", "read_export"]
+           "causal_net_dynamics_coupling", "CLR", "load_anndata", "read_export", "other_estimators"]
 __version__ = "0.1.0"

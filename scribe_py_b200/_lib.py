@@ -50,7 +50,7 @@ _lib_lock = threading.Lock()
 EXPORTS = [
     "scribe_abi_version", "scribe_last_error", "scribe_create", "scribe_destroy", "scribe_device_info",
     "scribe_get_stats", "scribe_estimate", "scribe_debug_counts", "scribe_upload_matrix", "scribe_lagged_jobs",
-    "scribe_lagged_jobs_dev", "scribe_upload_coupling", "scribe_coupling_jobs", "scribe_coupling_jobs_dev",
+    "scribe_lagged_jobs_dev", "scribe_mi_jobs", "scribe_upload_coupling", "scribe_coupling_jobs", "scribe_coupling_jobs_dev",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
         lib.scribe_upload_matrix.argtypes = [P, P, I64, I64, P, I32]
         lib.scribe_lagged_jobs.argtypes = [P, P, I64, C.POINTER(Opts), I32, P, P]
         lib.scribe_lagged_jobs_dev.argtypes = [P, P, I64, C.POINTER(Opts), I32, P, P]
+        lib.scribe_mi_jobs.argtypes = [P, P, P, I64, C.POINTER(Opts), P]
         lib.scribe_upload_coupling.argtypes = [P, P, P, I64, I64]
         lib.scribe_coupling_jobs.argtypes = [P, P, P, I64, I32, C.POINTER(Opts), P, P]
         lib.scribe_coupling_jobs_dev.argtypes = [P, P, P, I64, I32, C.POINTER(Opts), P, P]
@@ -206,6 +207,15 @@ class Handle:
         out = np.empty(len(jobs))
         rc = self._lib.scribe_lagged_jobs(self._h, _ptr(jobs), len(jobs), C.byref(opts), int(bool(differential)),
                                           _ptr(sc), _ptr(out))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return out
+
+    def mi_jobs(self, src, dst, opts):
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        out = np.empty(len(src))
+        rc = self._lib.scribe_mi_jobs(self._h, _ptr(src), _ptr(dst), len(src), C.byref(opts), _ptr(out))
         if rc != SCRIBE_OK:
             _raise(rc)
         return out

@@ -659,6 +659,37 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
     end_call(h);
 }
 
+void mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, const scribe_opts* o, double* out)
+{
+    check_opts(o);
+    if (o->estimator != SCRIBE_EST_MI) fail(SCRIBE_E_ARG, "mi jobs use the mi estimator");
+    if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
+    if (n_jobs < 0 || (n_jobs > 0 && (!src || !dst || !out))) fail(SCRIBE_E_ARG, "NULL jobs/out");
+    if (h->n_cells > 2000000) fail(SCRIBE_E_ARG, "too many cells");
+    begin_call(h);
+    h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1));
+    const int64_t N = h->n_cells;
+    for (int64_t pos = 0; pos < n_jobs; pos += 262144) {
+        const int64_t nj = std::min<int64_t>(262144, n_jobs - pos);
+        std::vector<JobDesc> hj(nj);
+        for (int64_t j = 0; j < nj; j++) {
+            const int a = src[pos + j], b = dst[pos + j];
+            if (a < 0 || a >= h->n_genes || b < 0 || b >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
+            std::memset(&hj[j], 0, sizeof(JobDesc));
+            hj[j].col[0] = h->E.as<double>() + (size_t)a * N;
+            hj[j].col[1] = h->E.as<double>() + (size_t)b * N;
+            hj[j].n = (int)N;
+            h->st.point_pairs += N * N;
+        }
+        run_jobs(h, hj, (int)N, 1, 1, 0, o, h->out.as<double>() + pos, false, nullptr, nullptr);
+    }
+    if (n_jobs > 0) {
+        CU(cudaMemcpyAsync(out, h->out.p, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, h->stream));
+        h->st.d2h_bytes += sizeof(double) * n_jobs;
+    }
+    end_call(h);
+}
+
 template <class F> int guarded(scribe_handle* h, F&& f) {
     if (!h) { g_err = "NULL handle"; return SCRIBE_E_ARG; }
     try { Guard g(h); f(); g_err.clear(); return SCRIBE_OK; }
@@ -775,6 +806,10 @@ int scribe_lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs,
 int scribe_lagged_jobs_dev(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* opts,
                            int32_t differential, const double* scales, double* out_dev) {
     return guarded(h, [&] { lagged_jobs(h, jobs, n_jobs, opts, differential, scales, out_dev, true); });
+}
+
+int scribe_mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, const scribe_opts* opts, double* out_host) {
+    return guarded(h, [&] { mi_jobs(h, src, dst, n_jobs, opts, out_host); });
 }
 
 int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, int64_t n_genes, int64_t n_cells) {

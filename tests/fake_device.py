@@ -35,6 +35,9 @@ class FakeHandle:
             out[j] = est(x, y, z)
         return out
 
+    def mi_jobs(self, src, dst, opts):
+        return np.array([o.mi(self.E[a], self.E[b]) for a, b in zip(src, dst)])
+
     def upload_coupling(self, S, Y):
         self.S, self.Y = np.asarray(S, dtype=float), np.asarray(Y, dtype=float)
 

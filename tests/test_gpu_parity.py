@@ -305,3 +305,18 @@ def test_sweep_zero_inflated_large(S):
         dist = np.abs(P - P[i]).max(axis=1)
         assert a["eps"][i] == np.sort(dist)[5]
         assert a["counts"][0][i] == (dist <= a["eps"][i]).sum() - 1
+
+
+def test_mi_network(S):
+    """other_estimators.mi: all ordered pairs in one submission == oracle mi per pair (symmetric by construction)"""
+    E = recipes.rdi_synthetic(5, 400, 6)
+    m = S.causal_model(pd.DataFrame(E, index=pd.Index(["g%d" % i for i in range(5)], name="GENE_ID")))
+    M = S.other_estimators.mi(m).to_numpy(dtype=float)
+    assert np.isnan(np.diag(M)).all()
+    for a in range(5):
+        for b in range(5):
+            if a != b:
+                assert abs(M[a, b] - o.mi(E[a], E[b])) < TOL_EXACT
+    assert np.allclose(M, M.T, equal_nan=True, atol=1e-12)
+    C = S.other_estimators.corr(m).to_numpy(dtype=float)
+    assert abs(C[0, 1] - np.corrcoef(E[0], E[1])[0, 1]) < 1e-12
