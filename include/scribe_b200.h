@@ -49,11 +49,12 @@ extern "C" {
 #define SCRIBE_DENSITY_KNN 1
 
 /* kernel path selection (testing / debugging) */
-#define SCRIBE_PATH_AUTO    0  /* sorted-sweep kernels for cmi/cumi when instantiated and N >= 256,
+#define SCRIBE_PATH_AUTO    0  /* strip kernels for cmi/cumi when instantiated and N >= 256,
                                   else the dense fused kernels, else the generic kernels          */
 #define SCRIBE_PATH_GENERIC 1  /* runtime-dimension kernels (any dx,dy,dz,k within the limits)     */
 #define SCRIBE_PATH_DENSE   2  /* dense fused kernels: every query visits every candidate          */
 #define SCRIBE_PATH_SWEEP   3  /* sorted-sweep kernels regardless of N                             */
+#define SCRIBE_PATH_STRIP   4  /* strip kernels (x-sorted z-strips + z-sweep) regardless of N       */
 
 typedef struct scribe_handle scribe_handle;
 

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("SCRIBE_B200_LIB") or os.path.join(_HERE, "lib", "libs
 SCRIBE_OK, E_ARG, E_LENGTH, E_CUDA, E_DOMAIN, E_STATE = 0, 1, 2, 3, 4, 5
 EST_MI, EST_CMI, EST_UMI, EST_CUMI = 0, 1, 2, 3
 DENSITY_KDE, DENSITY_KNN = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_DENSE, PATH_SWEEP = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_DENSE, PATH_SWEEP, PATH_STRIP = 0, 1, 2, 3, 4
 MAX_COND = 4
 
 
@@ -100,11 +100,11 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-_PATH_NAMES = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "dense": PATH_DENSE, "sweep": PATH_SWEEP}
+_PATH_NAMES = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "dense": PATH_DENSE, "sweep": PATH_SWEEP, "strip": PATH_STRIP}
 
 
 def default_path():
-    """Kernel path used by the drivers: SCRIBE_B200_PATH=auto|dense|sweep|generic (default auto)."""
+    """Kernel path used by the drivers: SCRIBE_B200_PATH=auto|dense|sweep|strip|generic (default auto)."""
     return _PATH_NAMES[os.environ.get("SCRIBE_B200_PATH", "auto").lower()]
 
 

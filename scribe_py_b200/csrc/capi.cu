@@ -55,7 +55,7 @@ struct scribe_handle {
     // workspaces
     DevBuf psi; int psi_n = 0;
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
-    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS;
+    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips;
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
@@ -150,6 +150,31 @@ SweepFn pick_sweep(int dx, int dy, int dz, int kcap, bool weighted) {
     }
     return nullptr;
 }
+using StripFn = void (*)(const JobDesc*, int, int, const double*, double*, PointOut, unsigned long long*);
+using StripSortFn = void (*)(JobDesc*, int, int, double*, int64_t, int64_t);
+template <int DZ>
+StripFn pick_strip_k(int kcap, bool weighted) {
+    if (kcap == 6)  return weighted ? ksg_strip_kernel<DZ, 6, true>  : ksg_strip_kernel<DZ, 6, false>;
+    if (kcap == 16) return weighted ? ksg_strip_kernel<DZ, 16, true> : ksg_strip_kernel<DZ, 16, false>;
+    return nullptr;
+}
+StripFn pick_strip(int dx, int dy, int dz, int kcap, bool weighted) {
+    if (dx != 1 || dy != 1) return nullptr;
+    switch (dz) {
+        case 1: return pick_strip_k<1>(kcap, weighted);
+        case 2: return pick_strip_k<2>(kcap, weighted);
+        case 3: return pick_strip_k<3>(kcap, weighted);
+    }
+    return nullptr;
+}
+StripSortFn pick_strip_sort(int D) {
+    switch (D) {
+        case 3: return strip_sort_kernel<3>;
+        case 4: return strip_sort_kernel<4>;
+        case 5: return strip_sort_kernel<5>;
+    }
+    return nullptr;
+}
 constexpr int SWEEP_Q = 2;
 constexpr int SWEEP_MIN_N = 256;      // below this the dense kernel's single tile is at least as good
 
@@ -169,7 +194,7 @@ bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
     if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) return false;
     const int kcap = (o->k + 1 <= 6) ? 6 : ((o->k + 1 <= 16) ? 16 : 0);
     if (!kcap || !pick_sweep(dx, dy, dz, kcap, false)) return false;
-    if (o->path == SCRIBE_PATH_SWEEP) return true;
+    if (o->path == SCRIBE_PATH_SWEEP || o->path == SCRIBE_PATH_STRIP) return true;
     return o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N;
 }
 
@@ -238,7 +263,11 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     if (h->force_q) q = h->force_q;
     FusedFn fused = nullptr;
     SweepFn sweep = nullptr;
-    if (have_order && want_sweep(o, dx, dy, dz, n_max)) sweep = pick_sweep(dx, dy, dz, kcap, weighted);
+    StripFn strip = nullptr;
+    if (have_order && want_sweep(o, dx, dy, dz, n_max)) {
+        if (o->path != SCRIBE_PATH_SWEEP) strip = pick_strip(dx, dy, dz, kcap, weighted);
+        sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
+    }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     if (kcap == 16 && q == 4) q = 2;
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
@@ -329,7 +358,24 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     }
 
     // ---- estimator -----------------------------------------------------------------------------------
-    if (sweep) {
+    if (strip) {
+        const int spj = (n_max + STRIP - 1) / STRIP;                 // strips (= warps) per job
+        const int64_t npad = (int64_t)spj * STRIP;
+        const int64_t blk = strip_block_doubles(D, npad);
+        h->strips.ensure(sizeof(double) * (size_t)nj * blk);
+        h->partial.ensure(sizeof(double) * nj * spj);
+        CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * spj, h->stream));
+        StripSortFn ssort = pick_strip_sort(D);
+        const int64_t nwarps = nj * (int64_t)spj;
+        ssort<<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk, npad);
+        CU(cudaGetLastError());
+        const int bps = (spj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
+        strip<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, spj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
+        CU(cudaGetLastError());
+        finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), spj, (int)nj, out_dev);
+        CU(cudaGetLastError());
+        h->st.kernel_launches += 3; h->st.estimator_launches++;
+    } else if (sweep) {
         h->partial.ensure(sizeof(double) * nj * wpj);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * wpj, h->stream));
         const int bps = (wpj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
@@ -498,7 +544,8 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         std::vector<int> colidx;          // D per job
         int n_max = 0;
         int64_t end = pos;
-        size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0);
+        size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0)
+                         + (o->path == SCRIBE_PATH_AUTO || o->path == SCRIBE_PATH_STRIP ? (size_t)(D * 8 + 8) : 0);
         while (end < n_jobs && jobs[end].n_cond == L && (end - pos) < 262144) {
             const scribe_job& jb = jobs[end];
             if (jb.src < 0 || jb.src >= h->n_genes || jb.dst < 0 || jb.dst >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
@@ -615,7 +662,7 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
     }
     double* out_dev = out;
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (3 * N * 8))));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (7 * N * 8))));    // columns + strip index
     h->idx32a.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->idx32b.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->neff.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
@@ -740,7 +787,7 @@ void scribe_destroy(scribe_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
                       &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
-                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS})
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips})
         b->release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
     cudaStreamDestroy(h->stream);

@@ -31,6 +31,8 @@ struct JobDesc {
     const double* col[MAXD];  // x dims, then y dims, then z dims
     const double* w;          // uniformisation weights (cumi/umi) or nullptr; indexed like the columns
     const int32_t* perm;      // sweep kernels: rank -> row index, rows sorted ascending by the LAST column (nullptr = identity)
+    const double* strip;      // strip kernels: this job's x-sorted z-strips (see strip_sort_kernel), or nullptr
+    int64_t npad;             //   padded length (multiple of STRIP) of each strip column
     int64_t qoff;             // offset of this job's per-point outputs (eps/counts/...) in the workspace
     int32_t n;                // points
     int32_t pad;
@@ -653,6 +655,392 @@ ksg_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, con
     if (lane == 0) {
         partial[(size_t)job * warps_per_job + wj] = acc;
         if (visited) { atomicAdd(visited, nvis * 32ull * 32ull); atomicAdd(visited + 1, nvis2 * 32ull * 32ull); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strip kernels.  On expression data the conditioning coordinate z (the target's past) and y (its present) are strongly
+// correlated, so the z-window of a query holds hundreds of candidates while the (x, z) box holds ten to thirty: x, which
+// comes from another gene, is what prunes.  Each job therefore gets a small two-level index: its points in z-order
+// (JobDesc.perm, shared per target column) are cut into strips of STRIP consecutive z-ranks and every strip is sorted by
+// x (strip_sort_kernel, one warp per strip, per job: O(N log STRIP), negligible against O(N * window)).
+//   step A (lane-private): each query walks the strips outwards from its own, nearest first, and inside a strip visits
+//           only the x-range [x_i - bar, x_i + bar] found by binary search: the k-th neighbour distance (bar = running
+//           k-th distance, strict) and then n_xz, n_xyz (bar = eps, closed).  A side is abandoned when the strip's nearest
+//           z is already too far.  All tests are the reference's own subtractions, so the pruning is exact.
+//   step B (collective, the sweep machinery above): n_z and n_yz -- which no x-range can prune -- over the z-window,
+//           2 tests per visited pair instead of 4, one pass instead of two, queries regrouped by their true eps.
+// Workspace layout per job (doubles): D columns of npad values in strip order | npad int32 original indices |
+// 2 doubles per strip: z of its first and last rank.
+// ------------------------------------------------------------------------------------------------
+constexpr int STRIP = 64;
+
+__host__ __device__ inline int64_t strip_block_doubles(int D, int64_t npad) { return (int64_t)D * npad + npad / 2 + 2 * (npad / STRIP); }
+
+template <int D>
+__global__ void __launch_bounds__(64)
+strip_sort_kernel(JobDesc* __restrict__ jobs, int n_jobs, int strips_per_job, double* __restrict__ ws, int64_t block_doubles, int64_t npad)
+{
+    __shared__ double key[2][STRIP];
+    __shared__ int    id[2][STRIP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * 2 + wid;
+    const int job = (int)(gw / strips_per_job);
+    const int s = (int)(gw - (int64_t)job * strips_per_job);
+    if (job >= n_jobs) return;                                       // odd warp count: the last CTA's second warp is idle
+    JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    double* A = ws + (size_t)job * block_doubles;
+    if (s == 0 && lane == 0) { jd.strip = A; jd.npad = npad; }
+    if ((int64_t)s * STRIP >= npad) return;
+    const int base = s * STRIP;
+    double* K = key[wid]; int* I = id[wid];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int r = base + h * 32 + lane;
+        const int idx = r < n ? (jd.perm ? jd.perm[r] : r) : -1;
+        K[h * 32 + lane] = idx >= 0 ? jd.col[0][idx] : INFINITY;       // padding sorts last
+        I[h * 32 + lane] = idx;
+    }
+    __syncwarp();
+    // bitonic sort of 64 (key, id) pairs, one compare-exchange per lane and step
+    for (int k2 = 2; k2 <= STRIP; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const int i = 2 * j * (lane / j) + (lane % j);
+            const int p = i + j;
+            const bool up = (i & k2) == 0;
+            const double a = K[i], b = K[p];
+            const int ia = I[i], ib = I[p];
+            const bool sw = up ? (a > b) : (a < b);
+            if (sw) { K[i] = b; K[p] = a; I[i] = ib; I[p] = ia; }
+            __syncwarp();
+        }
+    }
+    int32_t* SI = reinterpret_cast<int32_t*>(A + (size_t)D * npad);
+    double* ED = A + (size_t)D * npad + npad / 2;
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int m = h * 32 + lane;
+        const int idx = I[m];
+        A[base + m] = K[m];
+        #pragma unroll
+        for (int c = 1; c < D; c++) A[(size_t)c * npad + base + m] = idx >= 0 ? jd.col[c][idx] : INFINITY;
+        SI[base + m] = idx;
+    }
+    if (lane == 0) {                                                     // z-range of the strip (z-ranks base .. base+cnt-1)
+        const int cnt = min(STRIP, n - base);
+        double zl = INFINITY, zh = -INFINITY;
+        if (cnt > 0) {
+            const int i0 = jd.perm ? jd.perm[base] : base, i1 = jd.perm ? jd.perm[base + cnt - 1] : base + cnt - 1;
+            zl = jd.col[D - 1][i0]; zh = jd.col[D - 1][i1];
+        }
+        ED[2 * s] = zl; ED[2 * s + 1] = zh;
+    }
+}
+
+template <int DZ, int KCAP, bool WEIGHTED>
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
+ksg_strip_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, const double* __restrict__ psi_tab,
+                 double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
+{
+    constexpr int D = 2 + DZ, KEY = D - 1, Q = 2, W = SWEEP_TPB / 32;
+    static_assert(STRIP == 32 * Q, "a warp owns exactly one strip");
+    __shared__ __align__(16) double sbuf[W][2 * D + 1][32];          // step A: [D][STRIP] strip image; step B: [D+1][32] chunk
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int bpj = (strips_per_job + W - 1) / W;
+    const int job = blockIdx.x / bpj;
+    const int s0  = (blockIdx.x - job * bpj) * W + wid;              // this warp's strip
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    if (s0 >= strips_per_job || s0 * STRIP >= n) return;            // warp-uniform; no CTA-level synchronisation below
+    const int nstrips = (n + STRIP - 1) / STRIP;
+    const int nchunks = (n + 31) / 32;
+    const int c0 = s0 * Q;
+    const int64_t np = jd.npad;
+    const double* __restrict__ A = jd.strip;
+    const int32_t* __restrict__ SI = reinterpret_cast<const int32_t*>(A + (size_t)D * np);
+    const double* __restrict__ ED = A + (size_t)D * np + np / 2;
+    double (*buf)[32] = sbuf[wid];
+
+    // queries = the strip's entries in x-order; padding (x = +inf) sorts last, idle slots shadow the first entry
+    double qc[Q][D], qw[Q];
+    int qidx[Q]; bool qok[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int r = s0 * STRIP + q * 32 + lane;
+        const int idx = SI[r];
+        qok[q] = idx >= 0;
+        const int rr = qok[q] ? r : s0 * STRIP;
+        qidx[q] = SI[rr];
+        #pragma unroll
+        for (int c = 0; c < D; c++) qc[q][c] = A[(size_t)c * np + rr];
+        qw[q] = 0.0;
+        if (WEIGHTED) qw[q] = jd.w[qidx[q]];
+    }
+
+    // ---------------- step A: walk over the x-sorted strips ----------------
+    // The warp visits strips collectively (own strip first, then outwards while some lane still needs the next one);
+    // each visited strip is staged in shared memory once, and every lane then searches ITS x-range in it privately
+    // (binary search + short scan in shared memory), so the work per strip is ~x-range, not STRIP, per query.
+    double (*sst)[STRIP] = reinterpret_cast<double (*)[STRIP]>(&sbuf[wid][0][0]);      // [D][STRIP] view (aliases buf)
+    auto stage_strip = [&](int s) {
+        const int base = s * STRIP;
+        __syncwarp();
+        #pragma unroll
+        for (int h = 0; h < 2; h++)
+            #pragma unroll
+            for (int c = 0; c < D; c++) sst[c][h * 32 + lane] = A[(size_t)c * np + base + h * 32 + lane];
+        __syncwarp();
+    };
+    unsigned long long nvis = 0;
+    double L[Q][KCAP];
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
+
+    auto knn_in_strip = [&](int s, bool own) {
+        const int cnt = min(STRIP, n - s * STRIP);
+        const double zedge = own ? 0.0 : (s < s0 ? ED[2 * s + 1] : ED[2 * s]);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double x = qc[q][0];
+            auto cand = [&](int m) {
+                ++nvis;
+                double dd = fabs(x - sst[0][m]);
+                bool l = dd < L[q][KCAP - 1];
+                #pragma unroll
+                for (int c = 1; c < D; c++) { const double a = fabs(qc[q][c] - sst[c][m]); l = l & (a < L[q][KCAP - 1]); dd = (a > dd) ? a : dd; }
+                if (l) topk_insert<KCAP>(L[q], dd);
+            };
+            if (qok[q] && (own || fabs(qc[q][KEY] - zedge) < L[q][KCAP - 1])) {
+                int ea = 0, eb = 0;
+                if (own) {      // seed with the x-neighbours (close in x, and in z by construction), then the rest of the strip
+                    const int p0 = q * 32 + lane;
+                    ea = max(0, p0 - (KCAP + 1)); eb = min(cnt, p0 + KCAP + 2);
+                    for (int m = ea; m < eb; m++) cand(m);
+                }
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (x - sst[0][mid] >= L[q][KCAP - 1]) lo = mid + 1; else hi = mid; }
+                for (int m = lo; m < cnt; m++) {
+                    if (m >= ea && m < eb) { m = eb - 1; continue; }
+                    if (sst[0][m] - x >= L[q][KCAP - 1]) break;
+                    cand(m);
+                }
+            }
+        }
+    };
+    // collective strip order shared by both walks: own strip, then outwards, alternating sides while both are needed
+    auto walk = [&](auto need, auto work) {
+        stage_strip(s0);
+        work(s0, true);
+        int sl = s0 - 1, sr = s0 + 1;
+        bool toggle = false;
+        while (true) {
+            bool al = false, ar = false;
+            if (sl >= 0)      al = __any_sync(0xffffffffu, need(ED[2 * sl + 1]));
+            if (sr < nstrips) ar = __any_sync(0xffffffffu, need(ED[2 * sr]));
+            if (!al && !ar) break;
+            const bool left = al && (!ar || toggle);
+            toggle = !toggle;
+            const int s = left ? sl-- : sr++;
+            stage_strip(s);
+            work(s, false);
+        }
+    };
+    walk([&](double zedge) { bool f = false;
+                             #pragma unroll
+                             for (int q = 0; q < Q; q++) f = f | (qok[q] & (fabs(qc[q][KEY] - zedge) < L[q][KCAP - 1]));
+                             return f; },
+         knn_in_strip);
+
+    double eps[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) eps[q] = L[q][KCAP - 1];             // +inf when n <= k, like cKDTree's padding
+
+    // n_xz, n_xyz over the same structure with the closed ball
+    int nxz[Q], nxyz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) nxz[q] = nxyz[q] = 0;
+    auto cnt_in_strip = [&](int s, bool own) {
+        const int cnt = min(STRIP, n - s * STRIP);
+        const double zedge = own ? 0.0 : (s < s0 ? ED[2 * s + 1] : ED[2 * s]);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double x = qc[q][0], e = eps[q];
+            if (qok[q] && (own || fabs(qc[q][KEY] - zedge) <= e)) {
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (x - sst[0][mid] > e) lo = mid + 1; else hi = mid; }
+                for (int m = lo; m < cnt; m++) {
+                    if (sst[0][m] - x > e) break;
+                    ++nvis;
+                    bool pz = true;
+                    #pragma unroll
+                    for (int c = 0; c < DZ; c++) pz = pz & (fabs(qc[q][2 + c] - sst[2 + c][m]) <= e);
+                    const bool py = fabs(qc[q][1] - sst[1][m]) <= e;
+                    nxz[q] += pz ? 1 : 0;
+                    nxyz[q] += (pz & py) ? 1 : 0;
+                }
+            }
+        }
+    };
+    walk([&](double zedge) { bool f = false;
+                             #pragma unroll
+                             for (int q = 0; q < Q; q++) f = f | (qok[q] & (fabs(qc[q][KEY] - zedge) <= eps[q]));
+                             return f; },
+         cnt_in_strip);
+
+    // ---------------- regroup the warp's queries by eps (slot 1 = the 32 sparsest), as in ksg_sweep_kernel ----------------
+    {
+        double* kb = &buf[0][0];
+        double key[Q]; int pos[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) key[q] = qok[q] ? eps[q] : INFINITY;
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) kb[q * 32 + lane] = key[q];
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) pos[q] = 0;
+        for (int j = 0; j < 32 * Q; j++) {
+            const double kj = kb[j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) pos[q] += ((kj < key[q]) | ((kj == key[q]) & (j < q * 32 + lane))) ? 1 : 0;
+        }
+        auto move = [&](double (&v)[Q]) {
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) kb[pos[q]] = v[q];
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = kb[q * 32 + lane];
+        };
+        double t[Q];
+        #pragma unroll
+        for (int c = 1; c < D; c++) {                                   // x is not needed any more
+            #pragma unroll
+            for (int q = 0; q < Q; q++) t[q] = qc[q][c];
+            move(t);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) qc[q][c] = t[q];
+        }
+        move(eps);
+        if (WEIGHTED) move(qw);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) t[q] = (double)(2 * (int64_t)qidx[q] + (qok[q] ? 1 : 0));
+        move(t);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { const int64_t c = (int64_t)t[q]; qidx[q] = (int)(c >> 1); qok[q] = (c & 1) != 0; }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) t[q] = (double)(((int64_t)nxz[q] << 24) + nxyz[q]);      // both < 2^24, exact in a double
+        move(t);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { const int64_t c = (int64_t)t[q]; nxz[q] = (int)(c >> 24); nxyz[q] = (int)(c & 0xffffff); }
+        __syncwarp();
+    }
+
+    // ---------------- step B: n_z, n_yz (and the weighted sums) over the z-window, collectively ----------------
+    int nyz[Q], nz[Q];
+    double wyz[Q], wz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
+
+    auto load_yz = [&](int chunk) {                                   // z-ordered chunk: y and z columns (+ weight) only
+        Chunk<D, WEIGHTED> c;
+        const int rank = chunk * 32 + lane;
+        const bool ok = rank < n;
+        const int idx = ok ? (jd.perm ? jd.perm[rank] : rank) : 0;
+        c.v[0] = 0.0;
+        #pragma unroll
+        for (int d = 1; d < D; d++) c.v[d] = ok ? jd.col[d][idx] : __longlong_as_double(0x7ff8000000000000LL);
+        c.w = 0.0;
+        if (WEIGHTED) c.w = ok ? jd.w[idx] : 0.0;
+        return c;
+    };
+    auto stage = [&](const Chunk<D, WEIGHTED>& c) {
+        __syncwarp();
+        #pragma unroll
+        for (int d = 1; d < D; d++) buf[d][lane] = c.v[d];
+        if (WEIGHTED) buf[D][lane] = c.w;
+        __syncwarp();
+    };
+    auto yz_body = [&](auto q_first) {
+        constexpr int Q0 = decltype(q_first)::value;
+        #pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            double cc[D];
+            #pragma unroll
+            for (int d = 1; d < D; d++) cc[d] = buf[d][j];
+            double wj_ = 0.0;
+            if (WEIGHTED) wj_ = buf[D][j];
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) {
+                bool pz = true;
+                #pragma unroll
+                for (int d = 0; d < DZ; d++) pz = pz & (fabs(qc[q][2 + d] - cc[2 + d]) <= eps[q]);
+                const bool pyz = pz & (fabs(qc[q][1] - cc[1]) <= eps[q]);
+                inc_if(nz[q], pz); inc_if(nyz[q], pyz);
+                if (WEIGHTED) { add_if(wz[q], wj_, pz); add_if(wyz[q], wj_, pyz); }
+            }
+        }
+    };
+    unsigned long long nvis2 = 0;
+    {
+        for (int c = c0; c < c0 + Q && c < nchunks; c++) { stage(load_yz(c)); yz_body(std::integral_constant<int, 0>{}); nvis2 += Q; }
+        int cl = c0 - 1, cr = c0 + Q;
+        bool toggle = false;
+        Chunk<D, WEIGHTED> Lc, Rc, cur;
+        if (cl >= 0) Lc = load_yz(cl);
+        if (cr < nchunks) Rc = load_yz(cr);
+        auto need = [&](double znext) { unsigned f = 0u;
+                                        #pragma unroll
+                                        for (int q = 0; q < Q; q++) f |= (fabs(qc[q][KEY] - znext) <= eps[q]) ? (1u << q) : 0u;
+                                        return f; };
+        while (true) {
+            unsigned al = 0, ar = 0;
+            if (cl >= 0)      al = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Lc.v[KEY], 31)));
+            if (cr < nchunks) ar = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Rc.v[KEY], 0)));
+            if (!al && !ar) break;
+            const bool left = al && (!ar || toggle);
+            toggle = !toggle;
+            const unsigned act = left ? al : ar;
+            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_yz(cl); }
+            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_yz(cr); }
+            stage(cur);
+            if (act & 1u) { yz_body(std::integral_constant<int, 0>{}); nvis2 += Q; }
+            else          { yz_body(std::integral_constant<int, Q - 1>{}); nvis2 += 1; }
+        }
+    }
+
+    // ---------------- digamma terms + per-warp partial ----------------
+    double acc = 0.0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        if (qok[q]) {
+            const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
+            const int64_t o = jd.qoff + qidx[q];
+            double term;
+            if (WEIGHTED) {
+                const double wi = qw[q];
+                const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
+                term = wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
+                if (po.wsum) { po.wsum[2 * o] = Wyz; po.wsum[2 * o + 1] = Wz; }
+            } else {
+                term = psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            }
+            acc += term;
+            if (po.eps) po.eps[o] = eps[q];
+            if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvis += __shfl_down_sync(0xffffffffu, nvis, o);
+    if (lane == 0) {
+        partial[(size_t)job * strips_per_job + s0] = acc;
+        if (visited) { atomicAdd(visited, nvis); atomicAdd(visited + 1, nvis2 * 32ull * 32ull); }
     }
 }
 

@@ -87,6 +87,6 @@ def ksg_debug(estimator, x, y, z=None, normalization=False, k=5, density_estimat
     z = None if z is None else _as2d(z)
     if normalization:
         x, y, z = _normalise(x, y, z)
-    p = {"auto": _lib.PATH_AUTO, "generic": _lib.PATH_GENERIC, "dense": _lib.PATH_DENSE, "sweep": _lib.PATH_SWEEP}[path]
+    p = _lib._PATH_NAMES[path]
     opts = _lib.make_opts(est, k, density_estimation_method, k_density, bw, p)
     return _handle().debug_counts(x, y, z, opts)

@@ -28,7 +28,7 @@ def close(got, ref, tol):
     return abs(got - ref) <= tol
 
 
-@pytest.mark.parametrize("path", ["auto", "generic", "dense", "sweep"])
+@pytest.mark.parametrize("path", ["auto", "generic", "dense", "sweep", "strip"])
 @pytest.mark.parametrize("name", list(SETS))
 def test_counts_bit_exact(S, golden, name, path):
     x, y, z = SETS[name]()
@@ -101,7 +101,7 @@ def test_error_behaviour(S):
     assert S.vd(3) == pytest.approx(o.vd(3), abs=1e-15)
 
 
-@pytest.mark.parametrize("path", ["dense", "sweep"])
+@pytest.mark.parametrize("path", ["dense", "sweep", "strip"])
 def test_random_sizes_against_oracle(S, path):
     """ragged sizes around the chunk / tile / CTA boundaries, continuous x,y and heavily tied z"""
     rng = np.random.default_rng(5)
@@ -121,10 +121,11 @@ def test_sweep_equals_dense_uniformised(S, name):
     (the KDE sweep drops terms below 2^-64 of a sum that is >= 1)"""
     x, y, z = SETS[name]()
     a = S.information_estimators.ksg_debug("cumi", x, y, z, path="dense")
-    b = S.information_estimators.ksg_debug("cumi", x, y, z, path="sweep")
-    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
-    assert np.allclose(a["weights"], b["weights"], rtol=1e-6, atol=0)
-    assert np.allclose(a["wsum"], b["wsum"], rtol=1e-6, atol=0)
+    for path in ("sweep", "strip"):
+        b = S.information_estimators.ksg_debug("cumi", x, y, z, path=path)
+        assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"]), path
+        assert np.allclose(a["weights"], b["weights"], rtol=1e-6, atol=0)
+        assert np.allclose(a["wsum"], b["wsum"], rtol=1e-6, atol=0)
 
 
 def test_dynamics_coupling_c1(S, golden):
@@ -211,7 +212,7 @@ def test_full_size_properties(S):
     assert (c[0] >= 5).all() and (c[0] == 5).mean() > 0.99
     assert (c[0] <= c[1]).all() and (c[0] <= c[2]).all() and (c[1] <= c[3]).all() and (c[2] <= c[3]).all()
     assert (c[3] <= len(x) - 1).all()
-    for path in ("generic", "dense", "sweep"):
+    for path in ("generic", "dense", "sweep", "strip"):
         g = S.information_estimators.ksg_debug("cmi", x, y, z, path=path)
         assert np.array_equal(g["eps"], d["eps"]) and np.array_equal(g["counts"], c), path
     perm = np.random.default_rng(0).permutation(len(x))
@@ -254,7 +255,7 @@ def test_stats_and_paths(S):
     x, y, z = E[0, :-1, None], E[1, 1:, None], E[1, :-1, None]
     n = len(x)
     vals = {}
-    for name, path in (("dense", S._lib.PATH_DENSE), ("sweep", S._lib.PATH_SWEEP)):
+    for name, path in (("dense", S._lib.PATH_DENSE), ("sweep", S._lib.PATH_SWEEP), ("strip", S._lib.PATH_STRIP)):
         vals[name] = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CMI, 5, path=path))
         st = h.stats()
         assert st["jobs"] == 1 and st["kernel_launches"] >= 2 and st["estimator_ms"] > 0
@@ -262,7 +263,7 @@ def test_stats_and_paths(S):
             assert st["visited_knn"] == n * n and st["visited_count"] == n * n
         else:
             assert 0 < st["visited_knn"] < n * n and 0 < st["visited_count"] < n * n
-    assert vals["dense"] == vals["sweep"] or abs(vals["dense"] - vals["sweep"]) < 1e-13
+    assert abs(vals["dense"] - vals["sweep"]) < 1e-13 and abs(vals["dense"] - vals["strip"]) < 1e-13
 
 
 @pytest.mark.parametrize("dz", [1, 2, 3])
@@ -278,15 +279,17 @@ def test_sweep_matrix_against_oracle(S, dz, k):
     P = np.concatenate((x, y, z), axis=1)
     ix, iy, iz = (0,), (1,), tuple(range(2, 2 + dz))
     eps, cnt = o.knn_counts(P, [ix + iy + iz, ix + iz, iy + iz, iz], k)
-    for path in ("sweep", "dense"):
+    for path in ("sweep", "dense", "strip"):
         d = S.information_estimators.ksg_debug("cmi", x, y, z, k=k, path=path)
         assert np.array_equal(d["eps"], eps), path
         assert np.array_equal(d["counts"], cnt), path
     h = S._lib.default_handle()
     v_sweep = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CUMI, k, bw=0.2, path=S._lib.PATH_SWEEP))
     v_dense = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CUMI, k, bw=0.2, path=S._lib.PATH_DENSE))
+    v_strip = h.estimate(x, y, z, S._lib.make_opts(S._lib.EST_CUMI, k, bw=0.2, path=S._lib.PATH_STRIP))
     ref = o.cumi(x, y, z, k=k, bw=0.2)
     assert abs(v_sweep - ref) < TOL_KDE and abs(v_dense - ref) < TOL_KDE and abs(v_sweep - v_dense) < 1e-7
+    assert abs(v_strip - v_sweep) < 1e-12
 
 
 def test_sweep_zero_inflated_large(S):
@@ -297,8 +300,9 @@ def test_sweep_zero_inflated_large(S):
     z = rng.gamma(2., 1., (n, 1)); z[rng.random((n, 1)) < 0.3] = 0
     y = z + 0.1 * rng.standard_normal((n, 1)); y[rng.random((n, 1)) < 0.1] = 0
     a = S.information_estimators.ksg_debug("cmi", x, y, z, path="dense")
-    b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
-    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    for path in ("sweep", "strip"):
+        b = S.information_estimators.ksg_debug("cmi", x, y, z, path=path)
+        assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"]), path
     assert (a["eps"] == 0).mean() > 0.002                     # the tie case (eps = 0) is actually exercised
     P = np.concatenate((x, y, z), axis=1)
     for i in (0, 17, 2999, 5999):
