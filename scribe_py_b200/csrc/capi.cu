@@ -59,6 +59,7 @@ struct scribe_handle {
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
+    int no_strip2 = 0;                    // SCRIBE_B200_NO_STRIP2=1: use the first strip form also for dz = 1 (tuning)
 };
 
 namespace {
@@ -265,7 +266,11 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     SweepFn sweep = nullptr;
     StripFn strip = nullptr;
     if (have_order && want_sweep(o, dx, dy, dz, n_max)) {
-        if (o->path != SCRIBE_PATH_SWEEP) strip = pick_strip(dx, dy, dz, kcap, weighted);
+        // Measured on B200 (tools/tune.py): the strip forms visit 5-10x fewer candidates but their lane-private loops run at
+        // the pace of the sparsest query of the warp, so they only beat the sweep for the weighted estimator at large N
+        // (cumi, N = 20 000: 17.4 vs 20.2 ms per 240 jobs); everywhere else AUTO keeps the sweep.
+        const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted && n_max >= 8192 && !h->no_strip2;
+        if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
@@ -365,13 +370,25 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         h->strips.ensure(sizeof(double) * (size_t)nj * blk);
         h->partial.ensure(sizeof(double) * nj * spj);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * spj, h->stream));
-        StripSortFn ssort = pick_strip_sort(D);
         const int64_t nwarps = nj * (int64_t)spj;
-        ssort<<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk, npad);
-        CU(cudaGetLastError());
         const int bps = (spj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
-        strip<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, spj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
-        CU(cudaGetLastError());
+        if (dz == 1 && !h->no_strip2) {                              // all four counts as range queries on two strip images
+            const int64_t blk2 = strip2_block_doubles(npad, weighted);
+            h->strips.ensure(sizeof(double) * (size_t)nj * blk2);
+            if (weighted) strip_sort2_kernel<true><<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk2, npad);
+            else          strip_sort2_kernel<false><<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk2, npad);
+            CU(cudaGetLastError());
+            StripFn s2 = kcap == 6 ? (weighted ? ksg_strip2_kernel<6, true> : ksg_strip2_kernel<6, false>)
+                                   : (weighted ? ksg_strip2_kernel<16, true> : ksg_strip2_kernel<16, false>);
+            s2<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, spj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
+            CU(cudaGetLastError());
+        } else {
+            StripSortFn ssort = pick_strip_sort(D);
+            ssort<<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk, npad);
+            CU(cudaGetLastError());
+            strip<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, spj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
+            CU(cudaGetLastError());
+        }
         finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), spj, (int)nj, out_dev);
         CU(cudaGetLastError());
         h->st.kernel_launches += 3; h->st.estimator_launches++;
@@ -545,7 +562,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         int n_max = 0;
         int64_t end = pos;
         size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0)
-                         + (o->path == SCRIBE_PATH_AUTO || o->path == SCRIBE_PATH_STRIP ? (size_t)(D * 8 + 8) : 0);
+                         + (o->path == SCRIBE_PATH_AUTO || o->path == SCRIBE_PATH_STRIP ? (size_t)(std::max(D, 8) * 8 + 8) : 0);
         while (end < n_jobs && jobs[end].n_cond == L && (end - pos) < 262144) {
             const scribe_job& jb = jobs[end];
             if (jb.src < 0 || jb.src >= h->n_genes || jb.dst < 0 || jb.dst >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
@@ -662,7 +679,7 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
     }
     double* out_dev = out;
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (7 * N * 8))));    // columns + strip index
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (12 * N * 8))));   // columns + strip images
     h->idx32a.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->idx32b.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->neff.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
@@ -773,6 +790,7 @@ int scribe_create(int device, scribe_handle** out) {
         CU(cudaEventCreate(&h->ev_call0)); CU(cudaEventCreate(&h->ev_call1));
         CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
         h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
+        if (const char* e = std::getenv("SCRIBE_B200_NO_STRIP2")) h->no_strip2 = std::atoi(e);
         if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) h->force_q = v; }
         cudaSetDevice(prev);
         *out = h;

@@ -1044,6 +1044,334 @@ ksg_strip_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Strip kernels, second form (one conditioning column, DZ = 1: RDI and dynamics coupling).  Besides the x-sorted image
+// of every z-strip, the job also gets a y-sorted image with the weights' prefix sums, so that ALL four ball counts become
+// range queries: a strip whose whole z-range lies inside the ball contributes (upper - lower bound) of a binary search in
+// y to n_yz, its size to n_z and prefix-sum differences to the weighted sums; only the (at most two, plus the own) strips
+// cut by the ball's z-boundary are examined entry by entry.  No candidate-by-candidate z-sweep remains:
+// per query the cost is O(strips in the ball * log STRIP + |(x,z) box|) instead of O(z-window).
+// Interior test: z-ranks are contiguous, so if fl|z_i - z_first| <= eps and fl|z_i - z_last| <= eps every entry of the
+// strip satisfies the reference's test fl|z_i - z_j| <= eps (rounding is monotone on either side of z_i).
+// Layout per job (doubles): image X = 3 columns (x | y | z, x-sorted) + npad/2 (original indices) ;
+// image Y = y | z (y-sorted) [+ w | exclusive prefix of w] ; 2 per strip: z of first / last rank ; [+ 1 per strip: sum w].
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t strip2_block_doubles(int64_t npad, bool weighted) {
+    return 3 * npad + npad / 2 + (weighted ? 4 : 2) * npad + (weighted ? 3 : 2) * (npad / STRIP);
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(64)
+strip_sort2_kernel(JobDesc* __restrict__ jobs, int n_jobs, int strips_per_job, double* __restrict__ ws, int64_t block_doubles, int64_t npad)
+{
+    __shared__ double key[2][STRIP];
+    __shared__ int    id[2][STRIP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * 2 + wid;
+    const int job = (int)(gw / strips_per_job);
+    const int s = (int)(gw - (int64_t)job * strips_per_job);
+    if (job >= n_jobs) return;
+    JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    double* A = ws + (size_t)job * block_doubles;
+    if (s == 0 && lane == 0) { jd.strip = A; jd.npad = npad; }
+    const int base = s * STRIP;
+    double* K = key[wid]; int* I = id[wid];
+    int32_t* SI = reinterpret_cast<int32_t*>(A + 3 * npad);
+    double* Y = A + 3 * npad + npad / 2;                              // image Y
+    const int ycols = WEIGHTED ? 4 : 2;
+    double* ED = Y + (size_t)ycols * npad;
+    double* TOT = ED + 2 * (npad / STRIP);
+
+    auto bitonic = [&]() {
+        for (int k2 = 2; k2 <= STRIP; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                const int i = 2 * j * (lane / j) + (lane % j);
+                const int p = i + j;
+                const bool up = (i & k2) == 0;
+                const double a = K[i], b = K[p];
+                const int ia = I[i], ib = I[p];
+                const bool sw = up ? (a > b) : (a < b);
+                if (sw) { K[i] = b; K[p] = a; I[i] = ib; I[p] = ia; }
+                __syncwarp();
+            }
+    };
+    int myidx[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int r = base + h * 32 + lane;
+        myidx[h] = r < n ? (jd.perm ? jd.perm[r] : r) : -1;
+    }
+    // ---- image X: sort by x
+    #pragma unroll
+    for (int h = 0; h < 2; h++) { K[h * 32 + lane] = myidx[h] >= 0 ? jd.col[0][myidx[h]] : INFINITY; I[h * 32 + lane] = myidx[h]; }
+    __syncwarp();
+    bitonic();
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int m = h * 32 + lane;
+        const int idx = I[m];
+        A[base + m] = K[m];
+        A[npad + base + m]     = idx >= 0 ? jd.col[1][idx] : INFINITY;
+        A[2 * npad + base + m] = idx >= 0 ? jd.col[2][idx] : INFINITY;
+        SI[base + m] = idx;
+    }
+    __syncwarp();
+    // ---- image Y: sort by y
+    #pragma unroll
+    for (int h = 0; h < 2; h++) { K[h * 32 + lane] = myidx[h] >= 0 ? jd.col[1][myidx[h]] : INFINITY; I[h * 32 + lane] = myidx[h]; }
+    __syncwarp();
+    bitonic();
+    double wv[2] = {0.0, 0.0};
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int m = h * 32 + lane;
+        const int idx = I[m];
+        Y[base + m] = K[m];
+        Y[npad + base + m] = idx >= 0 ? jd.col[2][idx] : INFINITY;
+        if (WEIGHTED) { wv[h] = idx >= 0 ? jd.w[idx] : 0.0; Y[2 * npad + base + m] = wv[h]; }
+    }
+    if (WEIGHTED) {                                                  // exclusive prefix of w over the strip (fixed order)
+        double inc0 = wv[0], inc1 = wv[1];
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+            if (lane >= o) { inc0 += t0; inc1 += t1; }
+        }
+        const double half = __shfl_sync(0xffffffffu, inc0, 31);
+        Y[3 * npad + base + lane]      = inc0 - wv[0];
+        Y[3 * npad + base + 32 + lane] = half + (inc1 - wv[1]);
+        if (lane == 31) TOT[s] = half + inc1;
+    }
+    if (lane == 0) {
+        const int cnt = min(STRIP, n - base);
+        double zl = INFINITY, zh = -INFINITY;
+        if (cnt > 0) {
+            const int i0 = jd.perm ? jd.perm[base] : base, i1 = jd.perm ? jd.perm[base + cnt - 1] : base + cnt - 1;
+            zl = jd.col[2][i0]; zh = jd.col[2][i1];
+        }
+        ED[2 * s] = zl; ED[2 * s + 1] = zh;
+    }
+}
+
+template <int KCAP, bool WEIGHTED>
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
+ksg_strip2_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, const double* __restrict__ psi_tab,
+                  double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
+{
+    constexpr int D = 3, Q = 2, W = SWEEP_TPB / 32;
+    constexpr int YC = WEIGHTED ? 4 : 2;
+    __shared__ __align__(16) double sbuf[W][4][STRIP];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int bpj = (strips_per_job + W - 1) / W;
+    const int job = blockIdx.x / bpj;
+    const int s0  = (blockIdx.x - job * bpj) * W + wid;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    if (s0 >= strips_per_job || s0 * STRIP >= n) return;
+    const int nstrips = (n + STRIP - 1) / STRIP;
+    const int64_t np = jd.npad;
+    const double* __restrict__ A = jd.strip;
+    const int32_t* __restrict__ SI = reinterpret_cast<const int32_t*>(A + 3 * np);
+    const double* __restrict__ Y = A + 3 * np + np / 2;
+    const double* __restrict__ ED = Y + (size_t)YC * np;
+    const double* __restrict__ TOT = ED + 2 * (np / STRIP);
+    double (*sst)[STRIP] = sbuf[wid];
+
+    double qc[Q][D], qw[Q];
+    int qidx[Q]; bool qok[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int r = s0 * STRIP + q * 32 + lane;
+        qok[q] = SI[r] >= 0;
+        const int rr = qok[q] ? r : s0 * STRIP;
+        qidx[q] = SI[rr];
+        #pragma unroll
+        for (int c = 0; c < D; c++) qc[q][c] = A[(size_t)c * np + rr];
+        qw[q] = 0.0;
+        if (WEIGHTED) qw[q] = jd.w[qidx[q]];
+    }
+
+    auto stage = [&](const double* img, int ncols, int s) {
+        const int base = s * STRIP;
+        __syncwarp();
+        for (int c = 0; c < ncols; c++) {
+            sst[c][lane]      = img[(size_t)c * np + base + lane];
+            sst[c][32 + lane] = img[(size_t)c * np + base + 32 + lane];
+        }
+        __syncwarp();
+    };
+    auto walk = [&](const double* img, int ncols, auto need, auto work) {
+        stage(img, ncols, s0);
+        work(s0, true);
+        int sl = s0 - 1, sr = s0 + 1;
+        bool toggle = false;
+        while (true) {
+            bool al = false, ar = false;
+            if (sl >= 0)      al = __any_sync(0xffffffffu, need(ED[2 * sl + 1]));
+            if (sr < nstrips) ar = __any_sync(0xffffffffu, need(ED[2 * sr]));
+            if (!al && !ar) break;
+            const bool left = al && (!ar || toggle);
+            toggle = !toggle;
+            const int s = left ? sl-- : sr++;
+            stage(img, ncols, s);
+            work(s, false);
+        }
+    };
+
+    // ---------------- k-th neighbour distance (image X) ----------------
+    unsigned long long nvis = 0;
+    double L[Q][KCAP];
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int t = 0; t < KCAP; t++) L[q][t] = (t < KCAP - 1 - k) ? -INFINITY : INFINITY;
+    auto knn_in_strip = [&](int s, bool own) {
+        const int cnt = min(STRIP, n - s * STRIP);
+        const double zedge = own ? 0.0 : (s < s0 ? ED[2 * s + 1] : ED[2 * s]);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double x = qc[q][0];
+            auto cand = [&](int m) {
+                ++nvis;
+                double dd = fabs(x - sst[0][m]);
+                bool l = dd < L[q][KCAP - 1];
+                #pragma unroll
+                for (int c = 1; c < D; c++) { const double a = fabs(qc[q][c] - sst[c][m]); l = l & (a < L[q][KCAP - 1]); dd = (a > dd) ? a : dd; }
+                if (l) topk_insert<KCAP>(L[q], dd);
+            };
+            if (qok[q] && (own || fabs(qc[q][2] - zedge) < L[q][KCAP - 1])) {
+                int ea = 0, eb = 0;
+                if (own) {
+                    const int p0 = q * 32 + lane;
+                    ea = max(0, p0 - (KCAP + 1)); eb = min(cnt, p0 + KCAP + 2);
+                    for (int m = ea; m < eb; m++) cand(m);
+                }
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (x - sst[0][mid] >= L[q][KCAP - 1]) lo = mid + 1; else hi = mid; }
+                for (int m = lo; m < cnt; m++) {
+                    if (m >= ea && m < eb) { m = eb - 1; continue; }
+                    if (sst[0][m] - x >= L[q][KCAP - 1]) break;
+                    cand(m);
+                }
+            }
+        }
+    };
+    walk(A, 3, [&](double zedge) { bool f = false;
+                                   #pragma unroll
+                                   for (int q = 0; q < Q; q++) f = f | (qok[q] & (fabs(qc[q][2] - zedge) < L[q][KCAP - 1]));
+                                   return f; },
+         knn_in_strip);
+    double eps[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) eps[q] = L[q][KCAP - 1];
+
+    auto need_eps = [&](double zedge) { bool f = false;
+                                        #pragma unroll
+                                        for (int q = 0; q < Q; q++) f = f | (qok[q] & (fabs(qc[q][2] - zedge) <= eps[q]));
+                                        return f; };
+
+    // ---------------- n_xz, n_xyz (image X, closed ball) ----------------
+    int nxz[Q], nxyz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) nxz[q] = nxyz[q] = 0;
+    walk(A, 3, need_eps, [&](int s, bool own) {
+        const int cnt = min(STRIP, n - s * STRIP);
+        const double zedge = own ? 0.0 : (s < s0 ? ED[2 * s + 1] : ED[2 * s]);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double x = qc[q][0], e = eps[q];
+            if (qok[q] && (own || fabs(qc[q][2] - zedge) <= e)) {
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (x - sst[0][mid] > e) lo = mid + 1; else hi = mid; }
+                for (int m = lo; m < cnt; m++) {
+                    if (sst[0][m] - x > e) break;
+                    ++nvis;
+                    const bool pz = fabs(qc[q][2] - sst[2][m]) <= e;
+                    const bool py = fabs(qc[q][1] - sst[1][m]) <= e;
+                    nxz[q] += pz ? 1 : 0;
+                    nxyz[q] += (pz & py) ? 1 : 0;
+                }
+            }
+        }
+    });
+
+    // ---------------- n_z, n_yz and the weighted sums (image Y) ----------------
+    int nyz[Q], nz[Q];
+    double wyz[Q], wz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { nyz[q] = nz[q] = 0; wyz[q] = wz[q] = 0.0; }
+    walk(Y, YC, need_eps, [&](int s, bool own) {
+        const int cnt = min(STRIP, n - s * STRIP);
+        const double zlo = ED[2 * s], zhi = ED[2 * s + 1];
+        double tot = 0.0;
+        if (WEIGHTED) tot = TOT[s];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double yq = qc[q][1], zq = qc[q][2], e = eps[q];
+            const bool in_lo = fabs(zq - zlo) <= e, in_hi = fabs(zq - zhi) <= e;
+            // the ball's z-range meets this strip iff its nearer end is inside (for the own strip: always)
+            const bool touches = own || (s < s0 ? in_hi : in_lo);
+            if (qok[q] && touches) {
+                int lb = 0, hi = cnt;                                   // y-range [lb, ub): first entry with y_q - y <= e ...
+                while (lb < hi) { const int mid = (lb + hi) >> 1; if (yq - sst[0][mid] > e) lb = mid + 1; else hi = mid; }
+                int ub = lb; hi = cnt;                                  // ... up to the first entry with y - y_q > e
+                while (ub < hi) { const int mid = (ub + hi) >> 1; if (sst[0][mid] - yq > e) hi = mid; else ub = mid + 1; }
+                if (in_lo && in_hi) {                                   // whole strip inside the ball in z
+                    nz[q] += cnt; nyz[q] += ub - lb;
+                    if (WEIGHTED) {
+                        wz[q] += tot;
+                        // exclusive prefix P[m] = sum_{m' < m} w; P[cnt] = tot
+                        const double pu = (ub < cnt) ? sst[3][ub] : tot;
+                        const double pl = (lb < cnt) ? sst[3][lb] : tot;
+                        wyz[q] += pu - pl;
+                    }
+                    nvis += 12;
+                } else {                                                // cut by the ball's boundary: entry by entry
+                    for (int m = 0; m < cnt; m++) {
+                        const bool pz = fabs(zq - sst[1][m]) <= e;
+                        const bool pyz = pz & (m >= lb) & (m < ub);
+                        nz[q] += pz ? 1 : 0; nyz[q] += pyz ? 1 : 0;
+                        if (WEIGHTED) { wz[q] += pz ? sst[2][m] : 0.0; wyz[q] += pyz ? sst[2][m] : 0.0; }
+                    }
+                    nvis += cnt;
+                }
+            }
+        }
+    });
+
+    // ---------------- digamma terms + per-warp partial ----------------
+    double acc = 0.0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        if (qok[q]) {
+            const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
+            const int64_t o = jd.qoff + qidx[q];
+            double term;
+            if (WEIGHTED) {
+                const double wi = qw[q];
+                const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
+                term = wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
+                if (po.wsum) { po.wsum[2 * o] = Wyz; po.wsum[2 * o + 1] = Wz; }
+            } else {
+                term = psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            }
+            acc += term;
+            if (po.eps) po.eps[o] = eps[q];
+            if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvis += __shfl_down_sync(0xffffffffu, nvis, o);
+    if (lane == 0) {
+        partial[(size_t)job * strips_per_job + s0] = acc;
+        if (visited) atomicAdd(visited, nvis);
+    }
+}
+
 // Gaussian KDE inverse densities, sorted sweep: terms with (z_i - z_j)^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
 // than 2^-KDE_CUT (= 2^-44) each against a sum that is >= 1 (the self term), so a side is abandoned once the nearest unvisited
 // candidate is that far in the key coordinate for every query of the warp.

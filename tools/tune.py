@@ -46,3 +46,5 @@ if __name__ == "__main__":
         run(16, 20000, [1], _lib.EST_CUMI)
         run(30, 5000, [1], _lib.EST_CMI)
         run(30, 5000, [1], _lib.EST_CUMI)
+    elif what == "big":
+        run(24, 20000, [1], _lib.EST_CMI, reps=1)
