@@ -103,7 +103,6 @@ FusedFn pick_q(int q) {
     switch (q) {
         case 1: return ksg_fused_kernel<DX, DY, DZ, KCAP, 1, W>;
         case 2: return ksg_fused_kernel<DX, DY, DZ, KCAP, 2, W>;
-        case 4: return ksg_fused_kernel<DX, DY, DZ, KCAP, 4, W>;
     }
     return nullptr;
 }
@@ -111,7 +110,7 @@ FusedFn pick_q(int q) {
 template <int DX, int DY, int DZ, bool W>
 FusedFn pick_kq(int kcap, int q) {
     if (kcap == 6)  return pick_q<DX, DY, DZ, 6, W>(q);
-    if (kcap == 16) return pick_q<DX, DY, DZ, 16, W>(q == 4 ? 2 : q);
+    if (kcap == 16) return pick_q<DX, DY, DZ, 16, W>(q);
     return nullptr;
 }
 
@@ -274,7 +273,6 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
-    if (kcap == 16 && q == 4) q = 2;
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
     const int wpj = (n_max + 32 * SWEEP_Q - 1) / (32 * SWEEP_Q);        // warps per job, sweep kernels
     unsigned long long* visited = nullptr;
@@ -292,10 +290,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
 
     h->jobs.ensure(sizeof(JobDesc) * nj);
     JobDesc* dj = h->jobs.as<JobDesc>();
-    if (n_on_device) {
-        // column pointers were produced on the host but n lives in the device copy (coupling prep wrote it):
-        // only refresh pointers by a second pass below; here the caller has already uploaded descs.
-    } else {
+    if (!n_on_device) {      // coupling: the caller uploaded the descriptors and coupling_prep_kernel wrote n into them
         CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
         h->st.h2d_bytes += sizeof(JobDesc) * nj;
     }
@@ -791,7 +786,7 @@ int scribe_create(int device, scribe_handle** out) {
         CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
         h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
         if (const char* e = std::getenv("SCRIBE_B200_NO_STRIP2")) h->no_strip2 = std::atoi(e);
-        if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) h->force_q = v; }
+        if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2) h->force_q = v; }
         cudaSetDevice(prev);
         *out = h;
         g_err.clear();

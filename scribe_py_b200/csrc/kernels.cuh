@@ -214,7 +214,7 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
     int    qi[Q];
     #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const int i = q0 + tid * Q + q;                    // a warp owns 32*Q CONSECUTIVE points (see j0 below)
+        const int i = q0 + tid * Q + q;
         qi[q] = i;
         const int ii = i < n ? i : n - 1;                  // idle slots shadow the last point (results dropped)
         #pragma unroll
@@ -222,12 +222,6 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
     }
 
     const int ntiles = (n + cap - 1) / cap;
-    // Candidates are visited starting AT this warp's own query points (first the tile that holds them, and inside
-    // it from the warp's first point, wrapping round): for pseudotime-ordered (autocorrelated) cells the temporal
-    // neighbours are close in the joint space too, so the k-th-distance threshold tightens within the first few
-    // dozen candidates and the top-k insert path is rarely taken afterwards.  Any order gives the same result.
-    const int tile0 = min(q0 / cap, ntiles - 1);
-    const int wq0 = q0 + (tid & ~31) * Q;                  // this warp's first query point
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     auto load_tile = [&](int t) {
@@ -255,13 +249,9 @@ ksg_fused_kernel(const JobDesc* __restrict__ jobs, int blocks_per_job, int k, in
 
     int cnt4 = 0;
     for (int tt = 0; tt < ntiles; tt++) {
-        int t = tile0 + tt; if (t >= ntiles) t -= ntiles;
-        cnt4 = load_tile(t);
-        int j = 0;
-        if (tt == 0) { j = (wq0 - t * cap) & ~3; if (j < 0 || j >= cnt4) j = 0; }
+        cnt4 = load_tile(tt);
         #pragma unroll 2
-        for (int it = 0; it < cnt4; it += 2, j += 2) {
-            if (j >= cnt4) j = 0;                           // wrap (cnt4 and the start are multiples of 4)
+        for (int j = 0; j < cnt4; j += 2) {
             double ad[2][Q][D];
             bool lt[2][Q];
             bool any = false;
