@@ -326,3 +326,17 @@ def test_mi_network(S):
     assert np.allclose(M, M.T, equal_nan=True, atol=1e-12)
     C = S.other_estimators.corr(m).to_numpy(dtype=float)
     assert abs(C[0, 1] - np.corrcoef(E[0], E[1])[0, 1]) < 1e-12
+
+
+def test_rdi_network_top100_ranking(S):
+    """a 12-gene RDI network (132 ordered pairs x 2 delays): values within tolerance and the top-100 edge ranking of
+    the MAX matrix identical to the oracle's"""
+    E = recipes.rdi_synthetic(12, 500, 11)
+    genes = ["g%02d" % i for i in range(12)]
+    r = S.causal_model(pd.DataFrame(E, index=pd.Index(genes, name="GENE_ID"))).rdi([1, 5])
+    ref = o.rdi([[E[g]] for g in range(12)], [1, 5])
+    for d in (1, 5):
+        assert np.allclose(r[d].to_numpy(dtype=float), ref[d], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    got, want = r["MAX"].to_numpy(dtype=float), ref["MAX"]
+    top = lambda A: np.argsort(-A, axis=None, kind="stable")[:100]
+    assert np.array_equal(top(got), top(want))

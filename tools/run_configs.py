@@ -28,6 +28,8 @@ def ar_panel(G, T, seed):
 
 
 def cpu_check(fn, argsets):
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:     # multi-GPU runs: parity is established at 1 GPU + tools/check_multi_gpu.py
+        return np.full(len(argsets), np.nan)
     from multiprocessing import get_context
     with get_context("fork").Pool(min(len(argsets), os.cpu_count() or 1)) as p:
         return np.array(p.map(fn, argsets))
@@ -42,10 +44,18 @@ def _cumi_job(a):
 
 
 def report(name, n_jobs, wall, stats, extra):
-    line = {"config": name, "jobs": int(n_jobs), "wall_s": wall, "evals_per_s": n_jobs / wall}
+    line = {"config": name, "jobs": int(n_jobs), "wall_s": wall, "evals_per_s": n_jobs / wall,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1"))}
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(line), flush=True)
     return line
+
+
+def barrier():
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch, torch.distributed as dist
+        dist.barrier(); torch.cuda.synchronize()
 
 
 def stats_acc():
@@ -71,7 +81,7 @@ def run_rdi(name, G, T, delays, uniform, seed, n_check, L=None):
     genes = ["g%04d" % i for i in range(G)]
     m = S.causal_model(pd.DataFrame(E, index=pd.Index(genes, name="GENE_ID")))
     h = _lib.default_handle()
-    t = time.perf_counter(); r = m.rdi(delays, uniformization=uniform); wall = time.perf_counter() - t
+    barrier(); t = time.perf_counter(); r = m.rdi(delays, uniformization=uniform); barrier(); wall = time.perf_counter() - t
     st = h.stats()
     n_jobs = G * (G - 1) * len(delays)
     rng = np.random.default_rng(0)
@@ -81,12 +91,12 @@ def run_rdi(name, G, T, delays, uniform, seed, n_check, L=None):
         x, y, z = ksg_oracle.lagged_columns([E[a]], [E[b]], d)
         args.append((x, y, z)); got.append(r[d].iloc[a, b])
     ref = cpu_check(_cumi_job if uniform else _cmi_job, args)
-    extra = {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+    extra = {"parity_max_abs_diff": float(np.nanmax(np.abs(ref - np.array(got)))) if WORLD == 1 else None, "parity_jobs": n_check,
              "estimator_ms": st["estimator_ms"], "visited_fraction": (st["visited_knn"] + st["visited_count"]) / max(2 * st["point_pairs"], 1),
              "note": "stats of the last chunk-call only" if False else ""}
     out = [report(name, n_jobs, wall, st, extra)]
     if L:
-        t = time.perf_counter(); c = m.crdi(L=L, uniformization=uniform); wall = time.perf_counter() - t
+        barrier(); t = time.perf_counter(); c = m.crdi(L=L, uniformization=uniform); barrier(); wall = time.perf_counter() - t
         st = h.stats()
         # parity of sampled cRDI jobs through the oracle's conditioning-set logic
         res = {d: r[d].to_numpy(dtype=float) for d in delays}
@@ -100,7 +110,7 @@ def run_rdi(name, G, T, delays, uniform, seed, n_check, L=None):
             args.append(ksg_oracle.crdi_columns(expr, int(a), int(b), d, cn, cd)); got.append(c.iloc[a, b])
         ref = cpu_check(_cumi_job if uniform else _cmi_job, args)
         out.append(report(name + " -> crdi(L=%d)" % L, G * (G - 1), wall, st,
-                          {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+                          {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()) if WORLD == 1 else None, "parity_jobs": n_check,
                            "estimator_ms": st["estimator_ms"],
                            "visited_fraction": (st["visited_knn"] + st["visited_count"]) / max(2 * st["point_pairs"], 1)}))
     return out
@@ -115,7 +125,8 @@ def run_c3(G, N, n_check):
     genes = ["g%04d" % i for i in range(G)]
     ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
     h = _lib.default_handle()
-    t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); wall = time.perf_counter() - t
+    S.causal_net_dynamics_coupling(recipes.FakeAnnData({"spliced": spl[:, :8], "velocity": vel[:, :8]}, genes[:8]))   # warm-up
+    barrier(); t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); barrier(); wall = time.perf_counter() - t
     st = h.stats()
     M = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
     s = (spl - spl.mean(0)) / (spl.max(0) - spl.min(0)); v = (vel - vel.mean(0)) / (vel.max(0) - vel.min(0))
@@ -127,12 +138,25 @@ def run_c3(G, N, n_check):
         args.append((x[keep], y[keep], z[keep])); got.append(M[a, b])
     ref = cpu_check(_cmi_job, args)
     return report("C3 dynamics coupling %d genes x %d cells" % (G, N), G * (G - 1), wall, st,
-                  {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()), "parity_jobs": n_check,
+                  {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()) if WORLD == 1 else None, "parity_jobs": n_check,
                    "estimator_ms_last_chunk": st["estimator_ms"], "mean_cells_kept": float(np.mean([len(a[0]) for a in args]))})
+
+
+def init_distributed():
+    """under torchrun: one rank per GPU; the drivers then shard the gene pairs and all-gather the results"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch, torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        os.environ["SCRIBE_B200_DEVICE"] = str(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return int(os.environ.get("RANK", "0")), world
 
 
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
+    RANK, WORLD = init_distributed()
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0)
@@ -141,14 +165,18 @@ if __name__ == "__main__":
     sc = a.scale
     lines = []
     h = _lib.default_handle()
-    print(json.dumps({"device": h.device_name, "sms": h.sm_count, "path": os.environ.get("SCRIBE_B200_PATH", "auto")}), flush=True)
+    if RANK == 0:
+        print(json.dumps({"device": h.device_name, "sms": h.sm_count, "path": os.environ.get("SCRIBE_B200_PATH", "auto"), "n_gpus": WORLD}), flush=True)
     for c in a.configs:
         if c == "c1": lines.append(run_c1())
         if c == "c2": lines += run_rdi("C2 RDI 100 genes x 2000 cells x delays {1,5,10}", 100, 2000, [1, 5, 10], False, 2, 32)
         if c == "c3": lines.append(run_c3(max(8, int(500 * sc)), 10000, 16))
         if c == "c4": lines += run_rdi("C4 RDI+cRDI(L=2) %d genes x 5000 cells" % max(8, int(200 * sc)), max(8, int(200 * sc)), 5000, [1, 5, 10], False, 4, 16, L=2)
         if c == "c5": lines += run_rdi("C5 uniformised RDI (cumi) %d genes x 20000 cells x 3 delays" % max(8, int(1000 * sc)), max(8, int(1000 * sc)), 20000, [1, 5, 10], True, 5, 4)
-    if a.out:
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+    if a.out and RANK == 0:
         with open(a.out, "w") as f:
             for l in lines:
                 f.write(json.dumps(l) + "\n")
