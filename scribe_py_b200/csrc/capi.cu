@@ -779,7 +779,7 @@ int scribe_create(int device, scribe_handle** out) {
         h->sm_count = p.multiProcessorCount;
         cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
         h->mem_bytes = p.totalGlobalMem;
-        std::snprintf(h->name, sizeof(h->name), "%s", p.name);
+        std::snprintf(h->name, sizeof(h->name), "%.127s", p.name);
         if (p.major < 10) { delete h; cudaSetDevice(prev); fail(SCRIBE_E_CUDA, "scribe_b200 is built for sm_100a only"); }
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->ev_call0)); CU(cudaEventCreate(&h->ev_call1));

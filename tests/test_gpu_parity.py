@@ -340,3 +340,23 @@ def test_rdi_network_top100_ranking(S):
     got, want = r["MAX"].to_numpy(dtype=float), ref["MAX"]
     top = lambda A: np.argsort(-A, axis=None, kind="stable")[:100]
     assert np.array_equal(top(got), top(want))
+
+
+def test_full_size_cumi_job(S):
+    """one C5-sized job (N = 19 999, z-scored, KDE bw = 0.01) through the path AUTO picks at that size (strip kernels):
+    eps and all four counts bit-identical to the float64 brute force, weights to 2e-6, the estimate to 1e-6"""
+    E = recipes.rdi_synthetic(3, 20000, 5)
+    E = (E - E.mean(axis=1, keepdims=True)) / E.std(axis=1, keepdims=True)
+    x, y, z = E[0, :-1, None], E[1, 1:, None], E[1, :-1, None]
+    P = np.concatenate((x, y, z), axis=1)
+    w = o.kde_weights(P[:, [0, 2]], 0.01)
+    eps, cnt, W = o.knn_counts(P, [(0, 1, 2), (0, 2), (1, 2), (2,)], 5, weights=w)
+    d = S.information_estimators.ksg_debug("cumi", x, y, z)
+    assert np.array_equal(d["eps"], eps) and np.array_equal(d["counts"], cnt)
+    assert np.allclose(d["weights"], w, rtol=2e-6, atol=0)
+    assert np.allclose(d["wsum"][0], W[2], rtol=2e-6) and np.allclose(d["wsum"][1], W[3], rtol=2e-6)
+    from scipy.special import digamma
+    ref = float(np.mean(w * digamma(cnt[0]) - w * digamma(cnt[1]) - w * digamma(W[2]) + w * digamma(W[3])))
+    assert abs(float(S.cumi(x, y, z)) - ref) < TOL_KDE
+    c = S.information_estimators.ksg_debug("cmi", x, y, z)              # the sweep at full size
+    assert np.array_equal(c["eps"], eps) and np.array_equal(c["counts"], cnt)
