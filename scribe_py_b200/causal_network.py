@@ -246,24 +246,28 @@ class causal_model(object):
         top_nodes, top_delays, top_values = self.__extract_top_incoming_nodes_delays(max_val, max_delay, k_nodes=L)
 
         mv = max_delay.to_numpy()
+        # Job table, target-major (a rank's slab then shares its targets' columns).  For a target b every source uses the
+        # same conditioning set -- top[b] minus its first minimal slot (causal_network.py:233-235) -- except the L+1
+        # sources that are themselves in top[b], which drop their own slot instead (:230-232).
         jobs = np.zeros(G * (G - 1), dtype=_lib.JOB_DTYPE)
         j = 0
-        for a_i, a in enumerate(node_ids):
-            for b_i, b in enumerate(node_ids):
-                if a_i == b_i:
-                    continue
-                nodes = list(top_nodes[b]); dls = list(top_delays[b])
-                if a in top_nodes[b]:                                   # causal_network.py:230-232
-                    drop = top_nodes[b].index(a)
-                else:                                                   # :233-235, first minimal slot
-                    drop = top_values[b].index(min(top_values[b]))
-                del nodes[drop]; del dls[drop]
-                if any(n is None for n in nodes):
-                    raise ValueError("crdi needs at least L+1 scored incoming regulators per target")
-                jobs["src"][j] = a_i; jobs["dst"][j] = b_i; jobs["delay"][j] = int(mv[a_i, b_i]); jobs["n_cond"][j] = L
-                for c in range(L):
-                    jobs["cond_gene"][j, c] = pos[nodes[c]]; jobs["cond_delay"][j, c] = int(dls[c])
-                j += 1
+        for b_i, b in enumerate(node_ids):
+            nodes, dls, vals = top_nodes[b], top_delays[b], top_values[b]
+            if any(nd is None for nd in nodes):
+                raise ValueError("crdi needs at least L+1 scored incoming regulators per target")
+            slot_gene = np.array([pos[nd] for nd in nodes], dtype=np.int32)
+            slot_delay = np.array([int(d) for d in dls], dtype=np.int32)
+            src = np.concatenate((np.arange(b_i, dtype=np.int32), np.arange(b_i + 1, G, dtype=np.int32)))
+            sl = slice(j, j + G - 1)
+            jobs["src"][sl] = src; jobs["dst"][sl] = b_i; jobs["n_cond"][sl] = L
+            jobs["delay"][sl] = mv[src, b_i].astype(np.int32)
+            keep = [s_ for s_ in range(L + 1) if s_ != vals.index(min(vals))]
+            jobs["cond_gene"][sl, :L] = slot_gene[keep]; jobs["cond_delay"][sl, :L] = slot_delay[keep]
+            for s_own, g_own in enumerate(slot_gene):                       # sources inside the top set
+                row = j + (g_own if g_own < b_i else g_own - 1)
+                keep_own = [s_ for s_ in range(L + 1) if s_ != s_own]
+                jobs["cond_gene"][row, :L] = slot_gene[keep_own]; jobs["cond_delay"][row, :L] = slot_delay[keep_own]
+            j += G - 1
         h = _lib.default_handle()
         h.upload_matrix(E, run_off)
         opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
