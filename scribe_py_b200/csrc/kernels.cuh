@@ -1044,10 +1044,11 @@ ksg_strip_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, co
 // Interior test: z-ranks are contiguous, so if fl|z_i - z_first| <= eps and fl|z_i - z_last| <= eps every entry of the
 // strip satisfies the reference's test fl|z_i - z_j| <= eps (rounding is monotone on either side of z_i).
 // Layout per job (doubles): image X = 3 columns (x | y | z, x-sorted) + npad/2 (original indices) ;
-// image Y = y | z (y-sorted) [+ w | exclusive prefix of w] ; 2 per strip: z of first / last rank ; [+ 1 per strip: sum w].
+// image Y = y | z (y-sorted) [+ w | exclusive prefix of w, y-order] | z in rank order [+ exclusive prefix of w, rank order] ;
+// 2 per strip: z of first / last rank ; [+ 1 per strip: sum w].
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline int64_t strip2_block_doubles(int64_t npad, bool weighted) {
-    return 3 * npad + npad / 2 + (weighted ? 4 : 2) * npad + (weighted ? 3 : 2) * (npad / STRIP);
+    return 3 * npad + npad / 2 + (weighted ? 6 : 3) * npad + (weighted ? 3 : 2) * (npad / STRIP);
 }
 
 template <bool WEIGHTED>
@@ -1069,7 +1070,8 @@ strip_sort2_kernel(JobDesc* __restrict__ jobs, int n_jobs, int strips_per_job, d
     double* K = key[wid]; int* I = id[wid];
     int32_t* SI = reinterpret_cast<int32_t*>(A + 3 * npad);
     double* Y = A + 3 * npad + npad / 2;                              // image Y
-    const int ycols = WEIGHTED ? 4 : 2;
+    const int ycols = WEIGHTED ? 6 : 3;
+    const int zzc = WEIGHTED ? 4 : 2;                                // column of z in rank (= z) order
     double* ED = Y + (size_t)ycols * npad;
     double* TOT = ED + 2 * (npad / STRIP);
 
@@ -1133,6 +1135,26 @@ strip_sort2_kernel(JobDesc* __restrict__ jobs, int n_jobs, int strips_per_job, d
         Y[3 * npad + base + 32 + lane] = half + (inc1 - wv[1]);
         if (lane == 31) TOT[s] = half + inc1;
     }
+    {   // z (and the weights' prefix) in rank order: the ball cuts an edge strip at a rank found by binary search
+        double wr[2] = {0.0, 0.0};
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int idx = myidx[h];
+            Y[(size_t)zzc * npad + base + h * 32 + lane] = idx >= 0 ? jd.col[2][idx] : INFINITY;
+            if (WEIGHTED) wr[h] = idx >= 0 ? jd.w[idx] : 0.0;
+        }
+        if (WEIGHTED) {
+            double inc0 = wr[0], inc1 = wr[1];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+                if (lane >= o) { inc0 += t0; inc1 += t1; }
+            }
+            const double half = __shfl_sync(0xffffffffu, inc0, 31);
+            Y[(size_t)5 * npad + base + lane]      = inc0 - wr[0];
+            Y[(size_t)5 * npad + base + 32 + lane] = half + (inc1 - wr[1]);
+        }
+    }
     if (lane == 0) {
         const int cnt = min(STRIP, n - base);
         double zl = INFINITY, zh = -INFINITY;
@@ -1150,8 +1172,9 @@ ksg_strip2_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, c
                   double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
     constexpr int D = 3, Q = 2, W = SWEEP_TPB / 32;
-    constexpr int YC = WEIGHTED ? 4 : 2;
-    __shared__ __align__(16) double sbuf[W][4][STRIP];
+    constexpr int YC = WEIGHTED ? 6 : 3;
+    constexpr int ZZ = WEIGHTED ? 4 : 2;                              // image-Y column: z in rank order
+    __shared__ __align__(16) double sbuf[W][6][STRIP];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int bpj = (strips_per_job + W - 1) / W;
@@ -1318,14 +1341,22 @@ ksg_strip2_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, c
                         wyz[q] += pu - pl;
                     }
                     nvis += 12;
-                } else {                                                // cut by the ball's boundary: entry by entry
-                    for (int m = 0; m < cnt; m++) {
-                        const bool pz = fabs(zq - sst[1][m]) <= e;
-                        const bool pyz = pz & (m >= lb) & (m < ub);
-                        nz[q] += pz ? 1 : 0; nyz[q] += pyz ? 1 : 0;
-                        if (WEIGHTED) { wz[q] += pz ? sst[2][m] : 0.0; wyz[q] += pyz ? sst[2][m] : 0.0; }
+                } else {        // cut by the ball's boundary: n_z from the rank order (z ascending), n_yz over the y-range only
+                    int zl = 0; hi = cnt;
+                    while (zl < hi) { const int mid = (zl + hi) >> 1; if (zq - sst[ZZ][mid] > e) zl = mid + 1; else hi = mid; }
+                    int zu = zl; hi = cnt;
+                    while (zu < hi) { const int mid = (zu + hi) >> 1; if (sst[ZZ][mid] - zq > e) hi = mid; else zu = mid + 1; }
+                    nz[q] += zu - zl;
+                    if (WEIGHTED) {
+                        const double pu = (zu < cnt) ? sst[5][zu] : tot, pl = (zl < cnt) ? sst[5][zl] : tot;
+                        wz[q] += pu - pl;
                     }
-                    nvis += cnt;
+                    for (int m = lb; m < ub; m++) {
+                        const bool pyz = fabs(zq - sst[1][m]) <= e;
+                        nyz[q] += pyz ? 1 : 0;
+                        if (WEIGHTED) wyz[q] += pyz ? sst[2][m] : 0.0;
+                    }
+                    nvis += 12 + (ub - lb);
                 }
             }
         }

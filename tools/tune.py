@@ -48,3 +48,5 @@ if __name__ == "__main__":
         run(30, 5000, [1], _lib.EST_CUMI)
     elif what == "big":
         run(24, 20000, [1], _lib.EST_CMI, reps=1)
+    elif what == "c5one":
+        run(16, 20000, [1], _lib.EST_CUMI, reps=1)
