@@ -255,6 +255,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     if ((est == SCRIBE_EST_CMI || est == SCRIBE_EST_CUMI) && dz < 1) fail(SCRIBE_E_ARG, "cmi/cumi need a conditioning variable");
     const bool weighted = est >= SCRIBE_EST_UMI;
     const bool euclid = est == SCRIBE_EST_UMI;
+    if (weighted && n_on_device) fail(SCRIBE_E_ARG, "uniformised estimators are not available on the coupling path");
     ensure_psi(h, n_max);
 
     const int k = o->k;
@@ -332,7 +333,6 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
             h->st.kernel_launches++; h->st.estimator_launches++;
         } else {
             // sub-jobs over the density subspace, kNN-only generic kernel, then k/N/r^d
-            if (n_on_device) fail(SCRIBE_E_ARG, "kNN density is not available on the coupling path");
             std::vector<JobDesc> sub(hj);
             for (auto& s : sub) { for (int c = 0; c < dp; c++) s.col[c] = hj[&s - sub.data()].col[pd[c]]; s.w = nullptr; }
             h->pjobs.ensure(sizeof(JobDesc) * nj);
@@ -351,7 +351,6 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         CU(cudaGetLastError());
         h->st.kernel_launches++;
         // point every job at its weights
-        if (n_on_device) fail(SCRIBE_E_ARG, "uniformised estimators are not available on the coupling path");
         for (int64_t j = 0; j < nj; j++) hj[j].w = u + hj[j].qoff;
         CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
