@@ -50,7 +50,7 @@ extern "C" {
 
 /* kernel path selection (testing / debugging) */
 #define SCRIBE_PATH_AUTO    0  /* sorted-sweep kernels for cmi/cumi when instantiated and N >= 256 (strip kernels for
-                                  cumi with one conditioning column and N >= 8192),
+                                  cumi with one conditioning column),
                                   else the dense fused kernels, else the generic kernels          */
 #define SCRIBE_PATH_GENERIC 1  /* runtime-dimension kernels (any dx,dy,dz,k within the limits)     */
 #define SCRIBE_PATH_DENSE   2  /* dense fused kernels: every query visits every candidate          */

@@ -265,12 +265,16 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     FusedFn fused = nullptr;
     SweepFn sweep = nullptr;
     StripFn strip = nullptr;
+    bool use_strip2 = false;
     if (have_order && want_sweep(o, dx, dy, dz, n_max)) {
-        // Measured on B200 (tools/tune.py): the strip forms visit 5-10x fewer candidates but their lane-private loops run at
-        // the pace of the sparsest query of the warp, so they only beat the sweep for the weighted estimator at large N
-        // (cumi, N = 20 000: 17.4 vs 20.2 ms per 240 jobs); everywhere else AUTO keeps the sweep.
-        const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted && n_max >= 8192 && !h->no_strip2;
+        // Measured on B200 (tools/tune.py matrix, est_ms per batch, sweep / strip / strip2):
+        //   cmi   N=1000 2.51/2.60/2.93   2000 6.41/6.28/6.76   5000 11.9/15.5/15.3   10000 15.1/18.1/17.7   20000 25.4/28.1/27.1
+        //   cumi  N=1000 4.42/3.89/4.23   2000 11.1/9.05/9.18   5000 18.3/18.9/17.8   10000 23.1/22.4/20.8   20000 39.3/35.0/32.1
+        // The strip forms visit 5-10x fewer candidates, but their lane-private loops run at the pace of the sparsest query
+        // of the warp; they only pay where the sweep's count pass is heaviest, i.e. for the weighted estimator.
+        const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted;
         if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
+        use_strip2 = dz == 1 && !h->no_strip2 && (o->path == SCRIBE_PATH_STRIP || n_max >= 4096);
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
@@ -366,7 +370,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * spj, h->stream));
         const int64_t nwarps = nj * (int64_t)spj;
         const int bps = (spj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
-        if (dz == 1 && !h->no_strip2) {                              // all four counts as range queries on two strip images
+        if (use_strip2) {                                            // all four counts as range queries on two strip images
             const int64_t blk2 = strip2_block_doubles(npad, weighted);
             h->strips.ensure(sizeof(double) * (size_t)nj * blk2);
             if (weighted) strip_sort2_kernel<true><<<(unsigned)((nwarps + 1) / 2), 64, 0, h->stream>>>(dj, (int)nj, spj, h->strips.as<double>(), blk2, npad);

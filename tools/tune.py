@@ -50,3 +50,7 @@ if __name__ == "__main__":
         run(24, 20000, [1], _lib.EST_CMI, reps=1)
     elif what == "c5one":
         run(16, 20000, [1], _lib.EST_CUMI, reps=1)
+    elif what == "matrix":
+        for T, G in ((1000, 60), (2000, 60), (5000, 30), (10000, 20), (20000, 16)):
+            for est in (_lib.EST_CMI, _lib.EST_CUMI):
+                run(G, T, [1, 5], est, reps=1)
