@@ -228,7 +228,7 @@ def lagged_columns(runs_a, runs_b, delay, differential_mode=False):
     xs, ys, zs = [], [], []
     for ea, eb in zip(runs_a, runs_b):
         T = len(eb)
-        xs.append(ea[:len(ea) - delay])
+        xs.append(ea[:max(0, len(ea) - delay)])               # e[:-delay]: empty when the run is not longer than the delay
         zs.append(eb[delay - 1:T - 1])
         if differential_mode:
             ys.append(eb[delay - 1:T - 1] - eb[delay:T])      # previous minus current (cn:153)

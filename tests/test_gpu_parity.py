@@ -360,3 +360,18 @@ def test_full_size_cumi_job(S):
     assert abs(float(S.cumi(x, y, z)) - ref) < TOL_KDE
     c = S.information_estimators.ksg_debug("cmi", x, y, z)              # the sweep at full size
     assert np.array_equal(c["eps"], eps) and np.array_equal(c["counts"], cnt)
+
+
+def test_rdi_short_run_contributes_nothing(S):
+    """a run not longer than the delay contributes no samples (e[:-delay] is empty, causal_network.py:167-171)"""
+    rng = np.random.default_rng(3)
+    G = 3
+    runs = [rng.standard_normal((G, 400)).cumsum(axis=1) * 0.2 + rng.standard_normal((G, 400)), rng.standard_normal((G, 4))]
+    genes = ["a", "b", "c"]
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    r = m.rdi([1, 5])
+    ref = o.rdi([[run[g] for run in runs] for g in range(G)], [1, 5])
+    only_long = o.rdi([[runs[0][g]] for g in range(G)], [5])
+    for d in (1, 5):
+        assert np.allclose(r[d].to_numpy(dtype=float), ref[d], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    assert np.allclose(r[5].to_numpy(dtype=float), only_long[5], atol=TOL_EXACT, rtol=0, equal_nan=True)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tools/check_multi_gpu.py : sharded rdi() == unsharded rdi(), bit for bit."""
+"""torchrun --nproc-per-node N tools/check_multi_gpu.py : sharded rdi / crdi / uniformised rdi / dynamics coupling == unsharded, bit for bit."""
 import os, sys
 import numpy as np, pandas as pd, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,14 +16,23 @@ frame = pd.DataFrame(E, index=pd.Index(["g%02d" % i for i in range(12)], name="G
 m = S.causal_model(frame)
 r = m.rdi([1, 5])
 c = m.crdi(L=1)
+spl, vel, cgenes = recipes.gv_c()
+ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, cgenes)
+S.causal_net_dynamics_coupling(ad)
+cp = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
+u = m.rdi([1], uniformization=True)[1].to_numpy(dtype=float)
 # unsharded on this rank alone
 real_world = D.world
 D.world = lambda: (0, 1)
 m1 = S.causal_model(frame)
 r1 = m1.rdi([1, 5]); c1 = m1.crdi(L=1)
+ad1 = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, cgenes)
+S.causal_net_dynamics_coupling(ad1)
+cp1 = ad1.uns["causal_net"]["RDI"].to_numpy(dtype=float)
+u1 = m1.rdi([1], uniformization=True)[1].to_numpy(dtype=float)
 D.world = real_world
 ok = all(np.array_equal(r[d].to_numpy(), r1[d].to_numpy(), equal_nan=True) for d in (1, 5, "MAX")) and \
-    np.array_equal(c.to_numpy(), c1.to_numpy(), equal_nan=True)
+    np.array_equal(c.to_numpy(), c1.to_numpy(), equal_nan=True) and np.array_equal(cp, cp1) and np.array_equal(u, u1, equal_nan=True)
 t = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if dist.get_rank() == 0:
     print("multi-gpu invariance (world=%d): %s" % (dist.get_world_size(), "OK bit-identical" if t.item() == 1.0 else "MISMATCH"))
