@@ -3,6 +3,7 @@
 // entry point fails.
 #include "../../include/scribe_b200.h"
 #include "kernels.cuh"
+#include "sweep_window.cuh"
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
@@ -59,6 +60,7 @@ struct scribe_handle {
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
+    int sweep_v1 = 0;                     // SCRIBE_B200_SWEEP_V1=1: first sweep form (FP64 scan in both passes) for unweighted jobs too
     int no_strip2 = 0;                    // SCRIBE_B200_NO_STRIP2=1: use the first strip form also for dz = 1 (tuning)
 };
 
@@ -148,6 +150,13 @@ SweepFn pick_sweep(int dx, int dy, int dz, int kcap, bool weighted) {
         case 2: return weighted ? pick_sweep_k<2, true>(kcap) : pick_sweep_k<2, false>(kcap);
         case 3: return weighted ? pick_sweep_k<3, true>(kcap) : pick_sweep_k<3, false>(kcap);
     }
+    return nullptr;
+}
+// windowed sweep (sweep_window.cuh): unweighted estimators
+SweepFn pick_sweepw(int dx, int dy, int dz, int kcap) {
+    if (dx != 1 || dy != 1) return nullptr;
+    if (kcap == 6)  { if (dz == 1) return ksg_sweepw_kernel<1, 6, 2>;  if (dz == 2) return ksg_sweepw_kernel<2, 6, 2>;  if (dz == 3) return ksg_sweepw_kernel<3, 6, 2>; }
+    if (kcap == 16) { if (dz == 1) return ksg_sweepw_kernel<1, 16, 2>; if (dz == 2) return ksg_sweepw_kernel<2, 16, 2>; if (dz == 3) return ksg_sweepw_kernel<3, 16, 2>; }
     return nullptr;
 }
 using StripFn = void (*)(const JobDesc*, int, int, const double*, double*, PointOut, unsigned long long*);
@@ -265,7 +274,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     FusedFn fused = nullptr;
     SweepFn sweep = nullptr;
     StripFn strip = nullptr;
-    bool use_strip2 = false;
+    bool use_strip2 = false, windowed = false;
     if (have_order && want_sweep(o, dx, dy, dz, n_max)) {
         // Measured on B200 (tools/tune.py matrix, est_ms per batch, sweep / strip / strip2):
         //   cmi   N=1000 2.51/2.60/2.93   2000 6.41/6.28/6.76   5000 11.9/15.5/15.3   10000 15.1/18.1/17.7   20000 25.4/28.1/27.1
@@ -276,6 +285,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
         use_strip2 = dz == 1 && !h->no_strip2 && (o->path == SCRIBE_PATH_STRIP || n_max >= 4096);
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
+        if (!weighted && !h->sweep_v1) { sweep = pick_sweepw(dx, dy, dz, kcap); windowed = true; }
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
@@ -394,6 +404,11 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         h->partial.ensure(sizeof(double) * nj * wpj);
         CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nj * wpj, h->stream));
         const int bps = (wpj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
+        if (windowed) {                                              // FP32 pre-filter bound: per-job largest |coordinate|
+            job_absmax_kernel<<<(unsigned)nj, 128, 0, h->stream>>>(dj, D);
+            CU(cudaGetLastError());
+            h->st.kernel_launches++;
+        }
         sweep<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, wpj, k, h->psi.as<double>(), h->partial.as<double>(), po, visited);
         CU(cudaGetLastError());
         finalize_mean_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, h->partial.as<double>(), wpj, (int)nj, out_dev);
@@ -789,6 +804,7 @@ int scribe_create(int device, scribe_handle** out) {
         CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
         h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
         if (const char* e = std::getenv("SCRIBE_B200_NO_STRIP2")) h->no_strip2 = std::atoi(e);
+        if (const char* e = std::getenv("SCRIBE_B200_SWEEP_V1")) h->sweep_v1 = std::atoi(e);
         if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2) h->force_q = v; }
         cudaSetDevice(prev);
         *out = h;

@@ -36,6 +36,7 @@ struct JobDesc {
     int64_t qoff;             // offset of this job's per-point outputs (eps/counts/...) in the workspace
     int32_t n;                // points
     int32_t pad;
+    double absmax;            // windowed sweep: largest |coordinate| of the job, written on the device by job_absmax_kernel
 };
 
 struct PointOut {             // optional per-point outputs (debug entry point, generic path, kNN-only mode)

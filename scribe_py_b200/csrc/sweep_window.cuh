@@ -1,0 +1,439 @@
+// sweep_window.cuh -- second form of the sorted sweep (cmi, scalar x and y, 1..3 conditioning columns).
+//
+// Same contract as ksg_sweep_kernel (kernels.cuh): the points of a job are visited in the order of the LAST conditioning
+// column ("key"), a warp owns 32*Q consecutive ranks, results are bit-identical to the dense kernel.  Two changes cut the
+// FP64-pipe work per visited pair from 6 + 7 instructions to 0 + 4:
+//
+//   pass 1 (k-th neighbour distance, replaces tree_xyz.query(...)[0][k], information_estimators.py:165):
+//     the per-candidate scan is an FP32 *pre-filter* over the non-key coordinates.  A candidate is marked when
+//     |fl32(q_d) - fl32(c_d)| <= T for every non-key d, with T = ru32(thr*(1+2^-22) + absmax*2^-22 + 1e-37), thr the
+//     query's k-th distance at the start of the chunk and absmax the largest |coordinate| of the job
+//     (job_absmax_kernel).  T bounds every rounding the FP32 path can make, so the marked set is a superset of the
+//     candidates the FP64 test `max_d |q_d - c_d| < thr` accepts; each marked candidate is then re-tested in FP64,
+//     exactly as in the first sweep, before it enters the top-(k+1) list.  Unordered compares mark NaN/overflowed
+//     differences too, so a job whose absmax is huge or non-finite degrades to "mark everything", never to a wrong result.
+//
+//   pass 2 (the four ball counts, replaces 4 x query_ball_point, :169-172):
+//     every counted subspace contains the key, and the key is sorted, so the candidates with |key_i - key_j| <= eps_i
+//     are one contiguous rank window [lo_i, hi_i], found by two binary searches that use the very subtraction the dense
+//     kernel uses (monotone rounding => the same set).  Inside the warp's chunk range only the x and y (and extra z)
+//     differences are formed -- 2 DADD + 2 DSETP per pair -- and their outcomes are collected as one bit per candidate;
+//     the counts are popc(window & ...) once per chunk.  n_z for a single conditioning column is hi - lo + 1 - 1.
+//
+// Everything that decides a count is still FP64.
+#pragma once
+#include "kernels.cuh"
+
+namespace scribe {
+
+#ifndef SWEEPW_UNROLL
+#define SWEEPW_UNROLL 8
+#endif
+
+// largest |coordinate| over the D columns of each job -> JobDesc.absmax (one CTA per job; O(N*D) reads from L2)
+__global__ void __launch_bounds__(128)
+job_absmax_kernel(JobDesc* __restrict__ jobs, int D)
+{
+    __shared__ double red[4];
+    JobDesc& jd = jobs[blockIdx.x];
+    const int n = jd.n;
+    double m = 0.0;
+    bool bad = false;
+    for (int d = 0; d < D; d++) {
+        const double* __restrict__ c = jd.col[d];
+        for (int i = threadIdx.x; i < n; i += 128) { const double a = fabs(c[i]); bad |= !(a <= 1e30); m = (a > m) ? a : m; }
+    }
+    if (bad) m = INFINITY;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_down_sync(0xffffffffu, m, o); m = (t > m) ? t : m; }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; w++) m = (red[w] > m) ? red[w] : m;
+        jd.absmax = m;
+    }
+}
+
+// FP32 pre-filter step: mark `bit` unless some non-key difference is certainly above T (unordered-or-less-equal).
+template <int NP>
+__device__ __forceinline__ void knn_mark32(const float (&df)[NP], float T, unsigned bit, unsigned& mask)
+{
+    static_assert(NP >= 2 && NP <= 4, "2..4 non-key coordinates");
+    if (NP == 2)
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1;\n abs.f32 a0,%1; abs.f32 a1,%2;\n"
+            " setp.leu.f32 p, a0, %3;\n setp.leu.and.f32 p, a1, %3, p;\n @p or.b32 %0,%0,%4;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(T), "r"(bit));
+    else if (NP == 3)
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1,a2;\n abs.f32 a0,%1; abs.f32 a1,%2; abs.f32 a2,%3;\n"
+            " setp.leu.f32 p, a0, %4;\n setp.leu.and.f32 p, a1, %4, p;\n setp.leu.and.f32 p, a2, %4, p;\n @p or.b32 %0,%0,%5;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(df[NP > 2 ? 2 : 0]), "f"(T), "r"(bit));
+    else
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1,a2,a3;\n abs.f32 a0,%1; abs.f32 a1,%2; abs.f32 a2,%3; abs.f32 a3,%4;\n"
+            " setp.leu.f32 p, a0, %5;\n setp.leu.and.f32 p, a1, %5, p;\n setp.leu.and.f32 p, a2, %5, p;\n setp.leu.and.f32 p, a3, %5, p;\n"
+            " @p or.b32 %0,%0,%6;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(df[NP > 2 ? 2 : 0]), "f"(df[NP > 3 ? 3 : 0]), "f"(T), "r"(bit));
+}
+
+// pass-2 step: one bit per candidate and tested coordinate (closed ball, FP64): m |= bit when |d| <= e
+__device__ __forceinline__ void ball_bit(double d, double e, unsigned bit, unsigned& m)
+{
+    asm("{\n .reg .pred p;\n .reg .f64 a;\n abs.f64 a,%1;\n setp.le.f64 p, a, %2;\n @p or.b32 %0,%0,%3;\n}"
+        : "+r"(m) : "d"(d), "d"(e), "r"(bit));
+}
+__device__ __forceinline__ void ball_bit2(double d0, double d1, double e, unsigned bit, unsigned& m)
+{
+    asm("{\n .reg .pred p;\n .reg .f64 a,b;\n abs.f64 a,%1; abs.f64 b,%2;\n setp.le.f64 p, a, %3;\n setp.le.and.f64 p, b, %3, p;\n"
+        " @p or.b32 %0,%0,%4;\n}"
+        : "+r"(m) : "d"(d0), "d"(d1), "d"(e), "r"(bit));
+}
+
+// |v| without the FP64 pipe (fabs() of a value that feeds a select compiles to DADD -RZ,|v|)
+__device__ __forceinline__ double abs_f64(double v)
+{
+    return __hiloint2double(__double2hiint(v) & 0x7fffffff, __double2loint(v));
+}
+
+// bits [a, b] of a 32-bit word, for any integers a, b (empty when the range misses 0..31)
+__device__ __forceinline__ unsigned range_mask(int a, int b)
+{
+    a = max(a, 0); b = min(b, 31);
+    return (b >= a) ? ((0xffffffffu >> (31 - b + a)) << a) : 0u;
+}
+
+template <int DZ, int KCAP, int Q>
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
+ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
+                  double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
+{
+    static_assert(DZ >= 1 && DZ <= 3, "1..3 conditioning columns");
+    constexpr int D   = 2 + DZ;
+    constexpr int KEY = D - 1;
+    constexpr int NP  = D - 1;                    // non-key coordinates: x, y, z_0 .. z_{DZ-2}
+    constexpr int NPA = (NP + 1) & ~1;            // padded to a multiple of 2 -> 16-byte rows of doubles, 8/16-byte rows of floats
+    constexpr int W   = SWEEP_TPB / 32;
+    constexpr int UNR = SWEEPW_UNROLL;
+    constexpr int KL  = KCAP - 1;                 // list length: the k nearest OTHER points (the query itself is never inserted)
+    __shared__ __align__(16) double sd[W][32][NPA];          // candidates, non-key coordinates (FP64)
+    __shared__ __align__(16) float  sf[W][32][NPA];          // the same rounded to FP32 (pass 1 pre-filter)
+    __shared__ __align__(8)  double sk[W][32];               // candidates, key coordinate
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int bpj = (warps_per_job + W - 1) / W;
+    const int job = blockIdx.x / bpj;
+    const int wj  = (blockIdx.x - job * bpj) * W + wid;
+    const JobDesc& jd = jobs[job];
+    const int n = jd.n;
+    const int w0 = wj * 32 * Q;
+    if (wj >= warps_per_job || w0 >= n) return;                  // warp-uniform; nothing below synchronises the CTA
+    const int c0 = w0 / 32;
+    const int nchunks = (n + 31) / 32;
+    double (*bd)[NPA] = sd[wid];
+    float  (*bf)[NPA] = sf[wid];
+    double* bk = sk[wid];
+    const int32_t* __restrict__ perm = jd.perm;
+
+    double qc[Q][D];
+    float  qf[Q][NP];
+    int qidx[Q]; bool qok[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int rank = w0 + q * 32 + lane;
+        qok[q] = rank < n;
+        const int rr = qok[q] ? rank : n - 1;
+        qidx[q] = perm ? perm[rr] : rr;
+        #pragma unroll
+        for (int d = 0; d < D; d++) qc[q][d] = jd.col[d][qidx[q]];
+    }
+
+    auto stage = [&](const Chunk<D, false>& c, bool with_f32) {
+        __syncwarp();
+        #pragma unroll
+        for (int d = 0; d < NP; d += 2) {
+            double2 v; v.x = c.v[d]; v.y = (d + 1 < NP) ? c.v[d + 1] : 0.0;
+            *reinterpret_cast<double2*>(&bd[lane][d]) = v;
+        }
+        bk[lane] = c.v[KEY];
+        if (with_f32) {
+            #pragma unroll
+            for (int d = 0; d < NP; d += 2) {
+                float2 v; v.x = __double2float_rn(c.v[d]); v.y = (d + 1 < NP) ? __double2float_rn(c.v[d + 1]) : 0.f;
+                *reinterpret_cast<float2*>(&bf[lane][d]) = v;
+            }
+        }
+        __syncwarp();
+    };
+
+    // ---------------- pass 1: k-th neighbour distance ----------------
+    double L[Q][KL];
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int t = 0; t < KL; t++) L[q][t] = (t < KL - k) ? -INFINITY : INFINITY;
+    const double slack = jd.absmax * 0x1p-22 + 1e-37;           // +inf when the job's scale is not FP32-safe: everything is marked
+
+    // selfq: slot whose own points are the staged chunk (its lane-th candidate is the query itself and is skipped), or -1;
+    // fine: insert after every block of UNR candidates instead of once per chunk (centre chunks: the bar drops fast there)
+    auto knn_body = [&](auto q_first, int selfq, bool fine) {
+        constexpr int Q0 = decltype(q_first)::value;
+        unsigned mask[Q];
+        float T[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { mask[q] = 0u; T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack)); }
+        // blocks of UNR candidates: bits are set with immediates inside a block and shifted into place once per block
+        // (a fully unrolled scan does not fit the instruction cache next to the other phases: ncu no_inst 37 %)
+        #pragma unroll 1
+        for (int jb = 0; jb < 32; jb += UNR) {
+            unsigned mb[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) mb[q] = 0u;
+            #pragma unroll
+            for (int t = 0; t < UNR; t++) {
+                const int j = jb + t;
+                float cf[NPA];
+                if constexpr (NPA == 2) { const float2 v = *reinterpret_cast<const float2*>(&bf[j][0]); cf[0] = v.x; cf[1] = v.y; }
+                else          { const float4 v = *reinterpret_cast<const float4*>(&bf[j][0]); cf[0] = v.x; cf[1] = v.y; cf[2 % NPA] = v.z; cf[3 % NPA] = v.w; }
+                #pragma unroll
+                for (int q = Q0; q < Q; q++) {
+                    float df[NP];
+                    #pragma unroll
+                    for (int d = 0; d < NP; d++) df[d] = __fsub_rn(qf[q][d], cf[d]);
+                    knn_mark32<NP>(df, T[q], 1u << t, mb[q]);
+                }
+            }
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) mask[q] |= mb[q] << jb;
+            if (!fine && jb + UNR < 32) continue;
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) {
+                if (q == selfq) mask[q] &= ~(1u << lane);
+                while (mask[q]) {
+                    const int j = __ffs(mask[q]) - 1;
+                    mask[q] &= mask[q] - 1;
+                    double dd = abs_f64(qc[q][KEY] - bk[j]);
+                    #pragma unroll
+                    for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
+                    if (dd < L[q][KL - 1]) topk_insert<KL>(L[q], dd);          // exact test; NaN (padding) never passes
+                }
+                if (fine) T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack));
+            }
+        }
+    };
+    auto knn_chunk = [&](bool all) {
+        if (all) knn_body(std::integral_constant<int, 0>{}, -1, false); else knn_body(std::integral_constant<int, Q - 1>{}, -1, false);
+    };
+    auto set_qf = [&]() {
+        #pragma unroll
+        for (int q = 0; q < Q; q++)
+            #pragma unroll
+            for (int d = 0; d < NP; d++) qf[q][d] = __double2float_rn(qc[q][d]);
+    };
+
+    unsigned long long nvis = 0;
+    set_qf();
+    for (int c = c0; c < c0 + Q && c < nchunks; c++) { stage(load_chunk<D, false>(jd, c, lane, n), true); knn_body(std::integral_constant<int, 0>{}, c - c0, true); nvis += Q; }
+
+    // regroup the warp's queries by the k-th distance seen so far (see ksg_sweep_kernel): slot Q-1 gets the sparsest
+    if (Q > 1) {
+        double* kb = &bd[0][0];                                    // 32*NPA >= 32*Q doubles
+        static_assert(NPA >= Q, "scratch too small for the regroup");
+        double key[Q]; int pos[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) key[q] = qok[q] ? L[q][KL - 1] : INFINITY;
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) kb[q * 32 + lane] = key[q];
+        __syncwarp();
+        #pragma unroll
+        for (int q = 0; q < Q; q++) pos[q] = 0;
+        for (int j = 0; j < 32 * Q; j++) {
+            const double kj = kb[j];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) pos[q] += ((kj < key[q]) | ((kj == key[q]) & (j < q * 32 + lane))) ? 1 : 0;
+        }
+        auto move = [&](double (&v)[Q]) {
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) kb[pos[q]] = v[q];
+            __syncwarp();
+            #pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = kb[q * 32 + lane];
+        };
+        double t[Q];
+        #pragma unroll
+        for (int d = 0; d < D; d++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) t[q] = qc[q][d];
+            move(t);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) qc[q][d] = t[q];
+        }
+        #pragma unroll
+        for (int e = 0; e < KL; e++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) t[q] = L[q][e];
+            move(t);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) L[q][e] = t[q];
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) t[q] = (double)(2 * (int64_t)qidx[q] + (qok[q] ? 1 : 0));     // exact: < 2^32
+        move(t);
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { const int64_t c = (int64_t)t[q]; qidx[q] = (int)(c >> 1); qok[q] = (c & 1) != 0; }
+        __syncwarp();
+        set_qf();
+    }
+
+    {   // outward sweep: whichever side still has a candidate that some query needs (key distance below its k-th distance)
+        int cl = c0 - 1, cr = c0 + Q;
+        bool toggle = false;
+        Chunk<D, false> Lc, Rc, cur;
+        if (cl >= 0) Lc = load_chunk<D, false>(jd, cl, lane, n);
+        if (cr < nchunks) Rc = load_chunk<D, false>(jd, cr, lane, n);
+        auto need = [&](double znext) {
+            unsigned f = 0u;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) f |= (fabs(qc[q][KEY] - znext) < L[q][KL - 1]) ? (1u << q) : 0u;
+            return f;
+        };
+        while (true) {
+            unsigned al = 0, ar = 0;
+            if (cl >= 0)      al = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Lc.v[KEY], 31)));
+            if (cr < nchunks) ar = __reduce_or_sync(0xffffffffu, need(__shfl_sync(0xffffffffu, Rc.v[KEY], 0)));
+            if (!al && !ar) break;
+            const bool left = al && (!ar || toggle);
+            toggle = !toggle;
+            const unsigned act = left ? al : ar;
+            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, false>(jd, cl, lane, n); }
+            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, false>(jd, cr, lane, n); }
+            stage(cur, true);
+            const bool all = (act & ((1u << (Q - 1)) - 1u)) != 0u || Q == 1;
+            knn_chunk(all);
+            nvis += all ? Q : 1;
+        }
+    }
+
+    double eps[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) eps[q] = L[q][KL - 1];
+
+    // ---------------- pass 2: rank windows, then x / y (/ extra z) bits per candidate ----------------
+    int lo[Q], hi[Q];
+    {
+        // lo = first rank r with  key_r > key_i  or  |key_i - key_r| <= eps   (monotone false -> true in r)
+        // hi = last rank r with   key_r < key_i  or  |key_i - key_r| <= eps   (monotone true -> false in r)
+        int la[Q], lb[Q], ha[Q], hb[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { la[q] = 0; lb[q] = n; ha[q] = 0; hb[q] = n; }
+        const double* __restrict__ kcol = jd.col[KEY];
+        const int iters = 33 - __clz(n);
+        for (int it = 0; it < iters; it++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                if (la[q] < lb[q]) {
+                    const int mid = (la[q] + lb[q]) >> 1;
+                    const double zr = kcol[perm ? perm[mid] : mid];
+                    const bool A = (zr > qc[q][KEY]) || (fabs(qc[q][KEY] - zr) <= eps[q]);
+                    if (A) lb[q] = mid; else la[q] = mid + 1;
+                }
+                if (ha[q] < hb[q]) {
+                    const int mid = (ha[q] + hb[q]) >> 1;
+                    const double zr = kcol[perm ? perm[mid] : mid];
+                    const bool B = (zr < qc[q][KEY]) || (fabs(qc[q][KEY] - zr) <= eps[q]);
+                    if (B) ha[q] = mid + 1; else hb[q] = mid;
+                }
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { lo[q] = la[q]; hi[q] = ha[q] - 1; }
+    }
+    int nxyz[Q], nxz[Q], nyz[Q], nz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = 0; nz[q] = (DZ == 1) ? hi[q] - lo[q] + 1 : 0; }
+
+    int clo[Q], chi[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        clo[q] = __reduce_min_sync(0xffffffffu, lo[q] >> 5);
+        chi[q] = __reduce_max_sync(0xffffffffu, hi[q] >> 5);
+    }
+    int cmin = clo[0], cmax = chi[0];
+    #pragma unroll
+    for (int q = 1; q < Q; q++) { cmin = min(cmin, clo[q]); cmax = max(cmax, chi[q]); }
+
+    auto count_body = [&](auto q_first, int base) {
+        constexpr int Q0 = decltype(q_first)::value;
+        unsigned mx[Q], my[Q], mz[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; }
+        #pragma unroll 1
+        for (int jb = 0; jb < 32; jb += UNR) {
+            unsigned bx[Q], by[Q], bz[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; }
+            #pragma unroll
+            for (int t = 0; t < UNR; t++) {
+                const int j = jb + t;
+                double cc[NPA];
+                #pragma unroll
+                for (int d = 0; d < NPA; d += 2) { const double2 v = *reinterpret_cast<const double2*>(&bd[j][d]); cc[d] = v.x; cc[d + 1] = v.y; }
+                const unsigned bit = 1u << t;
+                #pragma unroll
+                for (int q = Q0; q < Q; q++) {
+                    ball_bit(qc[q][0] - cc[0], eps[q], bit, bx[q]);
+                    ball_bit(qc[q][1] - cc[1], eps[q], bit, by[q]);
+                    if (DZ == 2) ball_bit(qc[q][2] - cc[2], eps[q], bit, bz[q]);
+                    if (DZ == 3) ball_bit2(qc[q][2] - cc[2], qc[q][3 % D] - cc[3 % NPA], eps[q], bit, bz[q]);
+                }
+            }
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) { mx[q] |= bx[q] << jb; my[q] |= by[q] << jb; if (DZ > 1) mz[q] |= bz[q] << jb; }
+        }
+        #pragma unroll
+        for (int q = Q0; q < Q; q++) {
+            unsigned zw = range_mask(lo[q] - base, hi[q] - base);
+            if (DZ > 1) { zw &= mz[q]; nz[q] += __popc(zw); }
+            const unsigned xw = zw & mx[q];
+            nxz[q]  += __popc(xw);
+            nyz[q]  += __popc(zw & my[q]);
+            nxyz[q] += __popc(xw & my[q]);
+        }
+    };
+
+    unsigned long long nvis2 = 0;
+    {
+        Chunk<D, false> nxt = load_chunk<D, false>(jd, cmin, lane, n), cur;
+        for (int c = cmin; c <= cmax; c++) {
+            cur = nxt;
+            if (c < cmax) nxt = load_chunk<D, false>(jd, c + 1, lane, n);
+            stage(cur, false);
+            bool all = Q == 1;
+            #pragma unroll
+            for (int q = 0; q < Q - 1; q++) all |= (c >= clo[q]) & (c <= chi[q]);
+            if (all) count_body(std::integral_constant<int, 0>{}, c * 32);
+            else     count_body(std::integral_constant<int, Q - 1>{}, c * 32);
+            nvis2 += all ? Q : 1;
+        }
+    }
+
+    // ---------------- digamma terms + per-warp partial (fixed shuffle tree) ----------------
+    double acc = 0.0;
+    #pragma unroll
+    for (int q = 0; q < Q; q++) {
+        if (qok[q]) {
+            const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
+            const int64_t o = jd.qoff + qidx[q];
+            acc += psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            if (po.eps) po.eps[o] = eps[q];
+            if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        partial[(size_t)job * warps_per_job + wj] = acc;
+        if (visited) { atomicAdd(visited, nvis * 32ull * 32ull); atomicAdd(visited + 1, nvis2 * 32ull * 32ull); }
+    }
+}
+
+}  // namespace scribe

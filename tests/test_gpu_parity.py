@@ -375,3 +375,56 @@ def test_rdi_short_run_contributes_nothing(S):
     for d in (1, 5):
         assert np.allclose(r[d].to_numpy(dtype=float), ref[d], atol=TOL_EXACT, rtol=0, equal_nan=True)
     assert np.allclose(r[5].to_numpy(dtype=float), only_long[5], atol=TOL_EXACT, rtol=0, equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dz", [1, 2, 3])
+@pytest.mark.parametrize("scale", [1.0, 1e-42, 1e-30, 1e20, 1e35, 3e300])
+def test_windowed_sweep_extreme_scales(S, dz, scale):
+    """the FP32 pre-filter of the windowed sweep must stay a superset at any data scale: FP32-denormal (1e-42), FP32-overflow
+    (1e35: absmax > 1e30 marks everything; 3e300) and in between -- eps and counts bit-identical to the dense FP64 kernel"""
+    rng = np.random.default_rng(900 + dz)
+    n = 1100
+    z = rng.standard_normal((n, dz))
+    x = 0.4 * z[:, :1] + rng.standard_normal((n, 1))
+    y = x + z[:, -1:] + 0.3 * rng.standard_normal((n, 1))
+    x, y, z = x * scale, y * scale, z * scale
+    a = S.information_estimators.ksg_debug("cmi", x, y, z, path="dense")
+    b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
+    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    assert np.isfinite(a["eps"]).all() and (a["counts"][0] >= 5).all()
+
+
+@pytest.mark.gpu
+def test_windowed_sweep_fp32_collisions(S):
+    """coordinates that differ only below FP32 resolution (1 + j*2^-40) and an offset cluster (1e6 + small): the FP32 images
+    collide, the exact FP64 re-test must still order them; plus mixed magnitudes in one column"""
+    rng = np.random.default_rng(77)
+    n = 900
+    x = 1.0 + rng.integers(0, 4000, (n, 1)) * 2.0 ** -40
+    z = 1e6 + rng.standard_normal((n, 1)) * 1e-3
+    y = z - 1e6 + x + rng.standard_normal((n, 1)) * 1e-9
+    x[::7] *= 1e5                                              # mixed magnitudes
+    a = S.information_estimators.ksg_debug("cmi", x, y, z, path="dense")
+    b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
+    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    P = np.concatenate((x, y, z), axis=1)
+    eps, cnt = o.knn_counts(P, [(0, 1, 2), (0, 2), (1, 2), (2,)], 5)
+    assert np.array_equal(b["eps"], eps) and np.array_equal(b["counts"], cnt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [257, 1000, 4097])
+def test_windowed_sweep_vs_first_sweep_poisson(S, n):
+    """integer-count data (eps = 0 for most points, huge windows of tied keys): windowed sweep == dense == oracle"""
+    rng = np.random.default_rng(n)
+    x = rng.poisson(1.0, (n, 1)).astype(float)
+    z = rng.poisson(2.0, (n, 1)).astype(float)
+    y = (z + rng.poisson(0.5, (n, 1))).astype(float)
+    a = S.information_estimators.ksg_debug("cmi", x, y, z, path="dense")
+    b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
+    assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
+    if n <= 1000:
+        P = np.concatenate((x, y, z), axis=1)
+        eps, cnt = o.knn_counts(P, [(0, 1, 2), (0, 2), (1, 2), (2,)], 5)
+        assert np.array_equal(b["eps"], eps) and np.array_equal(b["counts"], cnt)

@@ -16,9 +16,9 @@ for ln in dis.split("\n"):
         infn = sub in ln; cur = None; continue
     if not infn:
         continue
-    m = re.search(r'//## File ".*?", line (\d+)', ln)
+    m = re.search(r'//## File "(.*?)", line (\d+)', ln)
     if m:
-        cur = int(m.group(1)); continue
+        cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/", ln)
     if m and cur is not None:
         amap[int(m.group(1), 16)] = cur
@@ -30,9 +30,14 @@ base = int(rows[0][ia], 16)
 ex, sm = Counter(), Counter()
 for r in rows:
     a = int(r[ia], 16) - base
-    ex[amap.get(a, -1)] += int(r[iex]); sm[amap.get(a, -1)] += int(r[ismp] or 0)
+    ex[amap.get(a, ("?", 0))] += int(r[iex]); sm[amap.get(a, ("?", 0))] += int(r[ismp] or 0)
 tot, ts = sum(ex.values()), sum(sm.values()) or 1
-lines = open(os.path.join(ROOT, "scribe_py_b200/csrc/kernels.cuh")).read().split("\n")
+files = {}
+def text(f, l):
+    if f not in files:
+        q = os.path.join(ROOT, "scribe_py_b200/csrc", f)
+        files[f] = open(q).read().split("\n") if os.path.exists(q) else None
+    return files[f][l - 1].strip()[:110] if files[f] and 0 < l <= len(files[f]) else "?"
 print("total warp instructions %.4g; mapped %d addresses" % (tot, len(amap)))
-for l, n in ex.most_common(top):
-    print("%5.2f%% inst %5.2f%% smp  L%4d  %s" % (100.0 * n / tot, 100.0 * sm[l] / ts, l, lines[l - 1].strip()[:120] if l > 0 else "?"))
+for (f, l), n in ex.most_common(top):
+    print("%5.2f%% inst %5.2f%% smp  %s:%d  %s" % (100.0 * n / tot, 100.0 * sm[(f, l)] / ts, f, l, text(f, l)))
