@@ -152,11 +152,20 @@ SweepFn pick_sweep(int dx, int dy, int dz, int kcap, bool weighted) {
     }
     return nullptr;
 }
-// windowed sweep (sweep_window.cuh): unweighted estimators
-SweepFn pick_sweepw(int dx, int dy, int dz, int kcap) {
+// windowed sweep (sweep_window.cuh)
+template <int DZ, bool W>
+SweepFn pick_sweepw_k(int kcap) {
+    if (kcap == 6)  return ksg_sweepw_kernel<DZ, 6, 2, W>;
+    if (kcap == 16) return ksg_sweepw_kernel<DZ, 16, 2, W>;
+    return nullptr;
+}
+SweepFn pick_sweepw(int dx, int dy, int dz, int kcap, bool weighted) {
     if (dx != 1 || dy != 1) return nullptr;
-    if (kcap == 6)  { if (dz == 1) return ksg_sweepw_kernel<1, 6, 2>;  if (dz == 2) return ksg_sweepw_kernel<2, 6, 2>;  if (dz == 3) return ksg_sweepw_kernel<3, 6, 2>; }
-    if (kcap == 16) { if (dz == 1) return ksg_sweepw_kernel<1, 16, 2>; if (dz == 2) return ksg_sweepw_kernel<2, 16, 2>; if (dz == 3) return ksg_sweepw_kernel<3, 16, 2>; }
+    switch (dz) {
+        case 1: return weighted ? pick_sweepw_k<1, true>(kcap) : pick_sweepw_k<1, false>(kcap);
+        case 2: return weighted ? pick_sweepw_k<2, true>(kcap) : pick_sweepw_k<2, false>(kcap);
+        case 3: return weighted ? pick_sweepw_k<3, true>(kcap) : pick_sweepw_k<3, false>(kcap);
+    }
     return nullptr;
 }
 using StripFn = void (*)(const JobDesc*, int, int, const double*, double*, PointOut, unsigned long long*);
@@ -276,16 +285,17 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     StripFn strip = nullptr;
     bool use_strip2 = false, windowed = false;
     if (have_order && want_sweep(o, dx, dy, dz, n_max)) {
-        // Measured on B200 (tools/tune.py matrix, est_ms per batch, sweep / strip / strip2):
-        //   cmi   N=1000 2.51/2.60/2.93   2000 6.41/6.28/6.76   5000 11.9/15.5/15.3   10000 15.1/18.1/17.7   20000 25.4/28.1/27.1
-        //   cumi  N=1000 4.42/3.89/4.23   2000 11.1/9.05/9.18   5000 18.3/18.9/17.8   10000 23.1/22.4/20.8   20000 39.3/35.0/32.1
+        // Measured on B200 (tools/tune.py matrix, est_ms per batch; first sweep / strip / strip2 / windowed sweep):
+        //   cmi   N=1000 2.51/2.60/2.93/2.11   2000 6.41/6.28/6.76/5.19   5000 11.9/15.5/15.3/8.99   10000 15.1/18.1/17.7/11.1   20000 25.4/28.1/27.1/18.4
+        //   cumi  N=1000 4.42/3.89/4.23/3.41   2000 11.1/9.05/9.18/7.87   5000 18.3/18.9/17.8/13.0   10000 23.1/22.4/20.8/16.2   20000 39.3/35.0/32.1/27.0
         // The strip forms visit 5-10x fewer candidates, but their lane-private loops run at the pace of the sparsest query
-        // of the warp; they only pay where the sweep's count pass is heaviest, i.e. for the weighted estimator.
-        const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted;
+        // of the warp; the windowed sweep (sweep_window.cuh) is the fastest form everywhere, so AUTO takes it for both
+        // estimators.  The first sweep and the strip forms stay selectable (SCRIBE_B200_SWEEP_V1=1, SCRIBE_PATH_STRIP).
+        const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted && h->sweep_v1;   // the windowed sweep beats both strip forms
         if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
         use_strip2 = dz == 1 && !h->no_strip2 && (o->path == SCRIBE_PATH_STRIP || n_max >= 4096);
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
-        if (!weighted && !h->sweep_v1) { sweep = pick_sweepw(dx, dy, dz, kcap); windowed = true; }
+        if (!h->sweep_v1) { sweep = pick_sweepw(dx, dy, dz, kcap, weighted); windowed = true; }
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;

@@ -29,6 +29,9 @@ namespace scribe {
 #ifndef SWEEPW_UNROLL
 #define SWEEPW_UNROLL 8
 #endif
+#ifndef SWEEPW_MIN_CTAS
+#define SWEEPW_MIN_CTAS 10                // 102 registers: 20 resident warps per SM; measured equal at N = 2000 and 8 % faster at N = 20 000 than 12 CTAs / 80 registers
+#endif
 
 // largest |coordinate| over the D columns of each job -> JobDesc.absmax (one CTA per job; O(N*D) reads from L2)
 __global__ void __launch_bounds__(128)
@@ -87,6 +90,30 @@ __device__ __forceinline__ void ball_bit2(double d0, double d1, double e, unsign
         : "+r"(m) : "d"(d0), "d"(d1), "d"(e), "r"(bit));
 }
 
+// weighted pass-2 steps (cumi): `win` holds the candidate's in-window bit at position `bit`.
+//   DZ == 1: y-ball inside the window -> by bit and W_yz += w          (W_z comes from prefix sums of the window)
+//   DZ  > 1: z-ball (extra conditioning columns) inside the window -> bz bit, W_z += w; then the y-ball inside it
+__device__ __forceinline__ void wball_y(double dy, double e, double w, unsigned win, unsigned bit, unsigned& by, double& wyz)
+{
+    asm("{\n .reg .pred pin,p;\n .reg .b32 t;\n .reg .f64 a;\n and.b32 t,%4,%5;\n setp.ne.u32 pin,t,0;\n abs.f64 a,%2;\n"
+        " setp.le.and.f64 p,a,%3,pin;\n @p add.f64 %1,%1,%6;\n @p or.b32 %0,%0,%5;\n}"
+        : "+r"(by), "+d"(wyz) : "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w));
+}
+__device__ __forceinline__ void wball_zy(double dz0, double dz1, bool two, double dy, double e, double w, unsigned win, unsigned bit,
+                                         unsigned& bz, unsigned& by, double& wz, double& wyz)
+{
+    if (two)
+        asm("{\n .reg .pred pz,py;\n .reg .b32 t;\n .reg .f64 a,b,c;\n and.b32 t,%8,%9;\n setp.ne.u32 pz,t,0;\n abs.f64 a,%4; abs.f64 b,%5; abs.f64 c,%6;\n"
+            " setp.le.and.f64 pz,a,%7,pz;\n setp.le.and.f64 pz,b,%7,pz;\n setp.le.and.f64 py,c,%7,pz;\n"
+            " @pz add.f64 %2,%2,%10;\n @pz or.b32 %0,%0,%9;\n @py add.f64 %3,%3,%10;\n @py or.b32 %1,%1,%9;\n}"
+            : "+r"(bz), "+r"(by), "+d"(wz), "+d"(wyz) : "d"(dz0), "d"(dz1), "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w));
+    else
+        asm("{\n .reg .pred pz,py;\n .reg .b32 t;\n .reg .f64 a,c;\n and.b32 t,%7,%8;\n setp.ne.u32 pz,t,0;\n abs.f64 a,%4; abs.f64 c,%5;\n"
+            " setp.le.and.f64 pz,a,%6,pz;\n setp.le.and.f64 py,c,%6,pz;\n"
+            " @pz add.f64 %2,%2,%9;\n @pz or.b32 %0,%0,%8;\n @py add.f64 %3,%3,%9;\n @py or.b32 %1,%1,%8;\n}"
+            : "+r"(bz), "+r"(by), "+d"(wz), "+d"(wyz) : "d"(dz0), "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w));
+}
+
 // |v| without the FP64 pipe (fabs() of a value that feeds a select compiles to DADD -RZ,|v|)
 __device__ __forceinline__ double abs_f64(double v)
 {
@@ -100,8 +127,8 @@ __device__ __forceinline__ unsigned range_mask(int a, int b)
     return (b >= a) ? ((0xffffffffu >> (31 - b + a)) << a) : 0u;
 }
 
-template <int DZ, int KCAP, int Q>
-__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_CTAS)
+template <int DZ, int KCAP, int Q, bool WEIGHTED>
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEPW_MIN_CTAS)
 ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                   double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
@@ -116,6 +143,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     __shared__ __align__(16) double sd[W][32][NPA];          // candidates, non-key coordinates (FP64)
     __shared__ __align__(16) float  sf[W][32][NPA];          // the same rounded to FP32 (pass 1 pre-filter)
     __shared__ __align__(8)  double sk[W][32];               // candidates, key coordinate
+    __shared__ __align__(8)  double sw[WEIGHTED ? W : 1][WEIGHTED ? 66 : 1];   // cumi: weights [0..31]; DZ == 1: their exclusive prefix sums at [32..64]
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int bpj = (warps_per_job + W - 1) / W;
@@ -130,9 +158,10 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     double (*bd)[NPA] = sd[wid];
     float  (*bf)[NPA] = sf[wid];
     double* bk = sk[wid];
+    double* bw = sw[WEIGHTED ? wid : 0];
     const int32_t* __restrict__ perm = jd.perm;
 
-    double qc[Q][D];
+    double qc[Q][D], qw[Q];
     float  qf[Q][NP];
     int qidx[Q]; bool qok[Q];
     #pragma unroll
@@ -143,9 +172,11 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         qidx[q] = perm ? perm[rr] : rr;
         #pragma unroll
         for (int d = 0; d < D; d++) qc[q][d] = jd.col[d][qidx[q]];
+        qw[q] = 0.0;
+        if (WEIGHTED) qw[q] = jd.w[qidx[q]];
     }
 
-    auto stage = [&](const Chunk<D, false>& c, bool with_f32) {
+    auto stage = [&](const Chunk<D, WEIGHTED>& c, bool with_f32) {
         __syncwarp();
         #pragma unroll
         for (int d = 0; d < NP; d += 2) {
@@ -158,6 +189,15 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             for (int d = 0; d < NP; d += 2) {
                 float2 v; v.x = __double2float_rn(c.v[d]); v.y = (d + 1 < NP) ? __double2float_rn(c.v[d + 1]) : 0.f;
                 *reinterpret_cast<float2*>(&bf[lane][d]) = v;
+            }
+        } else if (WEIGHTED) {
+            bw[lane] = c.w;
+            if (DZ == 1) {                                         // exclusive prefix sums of the chunk's weights: bw[32 + j] = w_0 + .. + w_{j-1}
+                double ps = c.w;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, ps, o); if (lane >= o) ps += t; }
+                bw[33 + lane] = ps;
+                if (lane == 0) bw[32] = 0.0;
             }
         }
         __syncwarp();
@@ -230,7 +270,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
 
     unsigned long long nvis = 0;
     set_qf();
-    for (int c = c0; c < c0 + Q && c < nchunks; c++) { stage(load_chunk<D, false>(jd, c, lane, n), true); knn_body(std::integral_constant<int, 0>{}, c - c0, true); nvis += Q; }
+    for (int c = c0; c < c0 + Q && c < nchunks; c++) { stage(load_chunk<D, WEIGHTED>(jd, c, lane, n), true); knn_body(std::integral_constant<int, 0>{}, c - c0, true); nvis += Q; }
 
     // regroup the warp's queries by the k-th distance seen so far (see ksg_sweep_kernel): slot Q-1 gets the sparsest
     if (Q > 1) {
@@ -275,6 +315,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             #pragma unroll
             for (int q = 0; q < Q; q++) L[q][e] = t[q];
         }
+        if (WEIGHTED) move(qw);
         #pragma unroll
         for (int q = 0; q < Q; q++) t[q] = (double)(2 * (int64_t)qidx[q] + (qok[q] ? 1 : 0));     // exact: < 2^32
         move(t);
@@ -287,9 +328,9 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     {   // outward sweep: whichever side still has a candidate that some query needs (key distance below its k-th distance)
         int cl = c0 - 1, cr = c0 + Q;
         bool toggle = false;
-        Chunk<D, false> Lc, Rc, cur;
-        if (cl >= 0) Lc = load_chunk<D, false>(jd, cl, lane, n);
-        if (cr < nchunks) Rc = load_chunk<D, false>(jd, cr, lane, n);
+        Chunk<D, WEIGHTED> Lc, Rc, cur;
+        if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
+        if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
         auto need = [&](double znext) {
             unsigned f = 0u;
             #pragma unroll
@@ -304,8 +345,8 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             const bool left = al && (!ar || toggle);
             toggle = !toggle;
             const unsigned act = left ? al : ar;
-            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, false>(jd, cl, lane, n); }
-            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, false>(jd, cr, lane, n); }
+            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
+            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
             stage(cur, true);
             const bool all = (act & ((1u << (Q - 1)) - 1u)) != 0u || Q == 1;
             knn_chunk(all);
@@ -361,29 +402,43 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     #pragma unroll
     for (int q = 1; q < Q; q++) { cmin = min(cmin, clo[q]); cmax = max(cmax, chi[q]); }
 
+    double wyz[Q], wz[Q];
+    #pragma unroll
+    for (int q = 0; q < Q; q++) wyz[q] = wz[q] = 0.0;
+
     auto count_body = [&](auto q_first, int base) {
         constexpr int Q0 = decltype(q_first)::value;
-        unsigned mx[Q], my[Q], mz[Q];
+        unsigned mx[Q], my[Q], mz[Q], zw[Q];
         #pragma unroll
-        for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; }
+        for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; zw[q] = range_mask(lo[q] - base, hi[q] - base); }
         #pragma unroll 1
         for (int jb = 0; jb < 32; jb += UNR) {
-            unsigned bx[Q], by[Q], bz[Q];
+            unsigned bx[Q], by[Q], bz[Q], zb[Q];
             #pragma unroll
-            for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; }
+            for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; zb[q] = zw[q] >> jb; }
             #pragma unroll
             for (int t = 0; t < UNR; t++) {
                 const int j = jb + t;
                 double cc[NPA];
                 #pragma unroll
                 for (int d = 0; d < NPA; d += 2) { const double2 v = *reinterpret_cast<const double2*>(&bd[j][d]); cc[d] = v.x; cc[d + 1] = v.y; }
+                double wj_ = 0.0;
+                if (WEIGHTED) wj_ = bw[j];
                 const unsigned bit = 1u << t;
                 #pragma unroll
                 for (int q = Q0; q < Q; q++) {
                     ball_bit(qc[q][0] - cc[0], eps[q], bit, bx[q]);
-                    ball_bit(qc[q][1] - cc[1], eps[q], bit, by[q]);
-                    if (DZ == 2) ball_bit(qc[q][2] - cc[2], eps[q], bit, bz[q]);
-                    if (DZ == 3) ball_bit2(qc[q][2] - cc[2], qc[q][3 % D] - cc[3 % NPA], eps[q], bit, bz[q]);
+                    if constexpr (!WEIGHTED) {
+                        ball_bit(qc[q][1] - cc[1], eps[q], bit, by[q]);
+                        if constexpr (DZ == 2) ball_bit(qc[q][2] - cc[2], eps[q], bit, bz[q]);
+                        if constexpr (DZ == 3) ball_bit2(qc[q][2] - cc[2], qc[q][3] - cc[3], eps[q], bit, bz[q]);
+                    } else if constexpr (DZ == 1) {
+                        wball_y(qc[q][1] - cc[1], eps[q], wj_, zb[q], bit, by[q], wyz[q]);
+                    } else if constexpr (DZ == 2) {
+                        wball_zy(qc[q][2] - cc[2], 0.0, false, qc[q][1] - cc[1], eps[q], wj_, zb[q], bit, bz[q], by[q], wz[q], wyz[q]);
+                    } else {
+                        wball_zy(qc[q][2] - cc[2], qc[q][3] - cc[3], true, qc[q][1] - cc[1], eps[q], wj_, zb[q], bit, bz[q], by[q], wz[q], wyz[q]);
+                    }
                 }
             }
             #pragma unroll
@@ -391,21 +446,33 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         }
         #pragma unroll
         for (int q = Q0; q < Q; q++) {
-            unsigned zw = range_mask(lo[q] - base, hi[q] - base);
-            if (DZ > 1) { zw &= mz[q]; nz[q] += __popc(zw); }
-            const unsigned xw = zw & mx[q];
-            nxz[q]  += __popc(xw);
-            nyz[q]  += __popc(zw & my[q]);
-            nxyz[q] += __popc(xw & my[q]);
+            if (!WEIGHTED) {
+                unsigned z = zw[q];
+                if (DZ > 1) { z &= mz[q]; nz[q] += __popc(z); }
+                const unsigned xw = z & mx[q];
+                nxz[q]  += __popc(xw);
+                nyz[q]  += __popc(z & my[q]);
+                nxyz[q] += __popc(xw & my[q]);
+            } else {                                             // my (and mz) already carry the window
+                const unsigned z = (DZ > 1) ? mz[q] : zw[q];
+                if (DZ > 1) nz[q] += __popc(z);
+                nxz[q]  += __popc(z & mx[q]);
+                nyz[q]  += __popc(my[q]);
+                nxyz[q] += __popc(my[q] & mx[q]);
+                if (DZ == 1) {
+                    const int a = max(lo[q] - base, 0), b = min(hi[q] - base, 31);
+                    if (b >= a) wz[q] += bw[33 + b] - bw[32 + a];
+                }
+            }
         }
     };
 
     unsigned long long nvis2 = 0;
     {
-        Chunk<D, false> nxt = load_chunk<D, false>(jd, cmin, lane, n), cur;
+        Chunk<D, WEIGHTED> nxt = load_chunk<D, WEIGHTED>(jd, cmin, lane, n), cur;
         for (int c = cmin; c <= cmax; c++) {
             cur = nxt;
-            if (c < cmax) nxt = load_chunk<D, false>(jd, c + 1, lane, n);
+            if (c < cmax) nxt = load_chunk<D, WEIGHTED>(jd, c + 1, lane, n);
             stage(cur, false);
             bool all = Q == 1;
             #pragma unroll
@@ -423,7 +490,14 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         if (qok[q]) {
             const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
             const int64_t o = jd.qoff + qidx[q];
-            acc += psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            if (WEIGHTED) {
+                const double wi = qw[q];
+                const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
+                acc += wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
+                if (po.wsum) { po.wsum[2 * o] = Wyz; po.wsum[2 * o + 1] = Wz; }
+            } else {
+                acc += psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
+            }
             if (po.eps) po.eps[o] = eps[q];
             if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
         }
