@@ -14,7 +14,7 @@ A "step" is one pass of the hot path over the whole job table.
           all-gather), timed with CUDA events, max over ranks.
   e2e   : the same through the public API, causal_model.rdi(delays), from a host DataFrame: host->device copy of
           the matrix and device->host read of the results inside the timed region.
-  roofline     : the dominant kernel (ksg_fused_kernel) against the ALU roofline north_star names: algorithmic
+  roofline     : the dominant kernel (ksg_sweepw_kernel) against the ALU roofline north_star names: algorithmic
                  FP32-pipe lane-ops (16 per point pair for D=3) / kernel time / (SMs x 128 lanes x clock).
   cpu_baseline : the reference-shaped CPU port (oracle/ref_port.py, same scipy calls and per-sample loops as the
                  reference) on a bounded sample of the same jobs, all host cores.
@@ -274,12 +274,17 @@ def ours_arm(args):
         # sorted sweep visits only the z-window of each query) x SURVEY 8(d)'s per-visit lane-ops: 6 in the kNN pass,
         # 10 in the count pass (D = 3).
         path = os.environ.get("SCRIBE_B200_PATH", "auto")
-        kernel = "ksg_sweep_kernel<1,1,1,6,2,false>" if path in ("auto", "sweep") else "ksg_fused_kernel<1,1,1,6,2,false>"
+        v1 = os.environ.get("SCRIBE_B200_SWEEP_V1", "0") not in ("", "0")
+        windowed = path in ("auto", "sweep") and not v1
+        kernel = ("ksg_sweepw_kernel<1,6,2,false>" if windowed else "ksg_sweep_kernel<1,1,1,6,2,false>") \
+            if path in ("auto", "sweep") else "ksg_fused_kernel<1,1,1,6,2,false>"
         k_ms = est_ms / max(est_launches, 1)
         pairs_per_launch = pairs / max(est_launches, 1)
         vk, vc = v_knn / max(est_launches, 1), v_cnt / max(est_launches, 1)
         achieved = (6.0 * vk + 10.0 * vc) / (k_ms * 1e-3)
-        achieved64 = (6.0 * vk + 7.0 * vc) / (k_ms * 1e-3)
+        # executed on the FP64 pipe per visit: first sweep / dense 6 (kNN) + 7 (count); windowed sweep 0 + 4 (its kNN scan
+        # is an FP32 pre-filter: 2 FADD + 2 FSETP, exact FP64 re-test only for marked candidates)
+        achieved64 = ((0.0 * vk + 4.0 * vc) if windowed else (6.0 * vk + 7.0 * vc)) / (k_ms * 1e-3)
         dense_equiv = OPS_PER_PAIR * pairs_per_launch / (k_ms * 1e-3)
         algo_bytes = 8.0 * 3 * CELLS * (n_jobs / world) + 8.0 * n_jobs / world
         value = n_jobs * args.steps / (dev_ms * 1e-3)
@@ -301,7 +306,8 @@ def ours_arm(args):
             "roofline": {"bound": "alu", "achieved": achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
                          "frac": achieved / alu_peak, "traffic": ncu_traffic(kernel) if n_gpus == 1 else None,
                          "kernel": kernel, "kernel_ms": k_ms, "kernel_share_of_step": est_ms / dev_ms,
-                         "algorithmic_ops": "6 per kNN-pass visit + 10 per count-pass visit (SURVEY 8d, D=3)",
+                         "algorithmic_ops": "6 per kNN-pass visit + 10 per count-pass visit (SURVEY 8d, D=3); the windowed sweep "
+                                            "executes 5 + 6 per visit (FP32 pre-filter; n_z from the rank window, no z test)",
                          "visits_per_launch": {"knn": vk, "count": vc, "dense_pairs_N2": pairs_per_launch,
                                                "visited_fraction": (vk + vc) / max(2.0 * pairs_per_launch, 1.0)},
                          "dense_equivalent": {"value": dense_equiv / 1e12, "frac_of_peak": dense_equiv / alu_peak,
@@ -310,14 +316,17 @@ def ours_arm(args):
                          "peak_source": "SMs x 128 FP32 lanes x sm_max_mhz from MEASURED_PEAKS.json (%s); FADD issue rate "
                                         "confirmed 3.89/4 warp-inst/clk/SM by tools/microbench.cu" % peak_src,
                          "fp64_pipe": {"achieved": achieved64 / 1e12, "peak": fp64_peak / 1e12, "frac": achieved64 / fp64_peak,
-                                       "unit": "Tlane-op/s", "note": "the kernel executes on the FP64 pipe (exact counts): "
-                                       "6 DADD/DSETP per kNN visit, 7 per count visit; peak = 64 lanes/clk/SM measured"},
+                                       "unit": "Tlane-op/s", "note": ("windowed sweep: FP32 pre-filter in the kNN pass (0 FP64 per visit, exact "
+                                                "re-test of marked candidates only), 2 DADD + 2 DSETP per count visit"
+                                                if windowed else
+                                                "the kernel executes on the FP64 pipe (exact counts): 6 DADD/DSETP per kNN visit, "
+                                                "7 per count visit") + "; peak = 64 lanes/clk/SM measured"},
                          "hbm": {"achieved_gbs": algo_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                                  "note": "non-binding: 3 columns x 8 B x N read per job"}},
         }
         if n_gpus == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            sample = cpu_jobs(E, max(8 * cores, 64), seed=0)
+            sample = cpu_jobs(E, max(24 * cores, 192), seed=0)
             cpu_pool(cores)
             cpu_vals, dt = run_cpu_sample(E, sample, cores)
             M = {d: np.full((G, G), np.nan) for d in DELAYS}
