@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
+OUT = sys.stdout
 DELAYS = [1, 5, 10]
 CELLS = 2000
 OPS_PER_PAIR = 16            # cmi/RDI, D = 3: 6 (kNN pass) + 10 (count pass) FP32-pipe lane-ops
@@ -171,7 +172,7 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -339,10 +340,19 @@ def ours_arm(args):
                                               "(cKDTree per-sample loops as the reference), multiprocessing over %d cores, %.1f s"
                                               % (len(sample), cores, dt),
                                     "parity_max_abs_diff_on_sample": float(np.abs(cpu_vals - gpu_vals).max())}
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _json_only_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; return a file object on the real
+    stdout so that the JSON line is the only thing the driver reads there."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -353,6 +363,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    global OUT
+    OUT = _json_only_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -162,7 +162,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     const int32_t* __restrict__ perm = jd.perm;
 
     double qc[Q][D], qw[Q];
-    float  qf[Q][NP];
+    unsigned long long qf2[Q][NPA / 2];           // FP32 images of the non-key query coordinates, packed in pairs
     int qidx[Q]; bool qok[Q];
     #pragma unroll
     for (int q = 0; q < Q; q++) {
@@ -229,15 +229,22 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             #pragma unroll
             for (int t = 0; t < UNR; t++) {
                 const int j = jb + t;
-                float cf[NPA];
-                if constexpr (NPA == 2) { const float2 v = *reinterpret_cast<const float2*>(&bf[j][0]); cf[0] = v.x; cf[1] = v.y; }
-                else          { const float4 v = *reinterpret_cast<const float4*>(&bf[j][0]); cf[0] = v.x; cf[1] = v.y; cf[2 % NPA] = v.z; cf[3 % NPA] = v.w; }
+                unsigned long long cf2[NPA / 2];                     // packed FP32 pairs: one FADD2 forms two differences
+                if constexpr (NPA == 2) { cf2[0] = *reinterpret_cast<const unsigned long long*>(&bf[j][0]); }
+                else { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&bf[j][0]); cf2[0] = v.x; cf2[NPA / 2 - 1] = v.y; }
                 #pragma unroll
                 for (int q = Q0; q < Q; q++) {
-                    float df[NP];
+                    float df[NPA];
                     #pragma unroll
-                    for (int d = 0; d < NP; d++) df[d] = __fsub_rn(qf[q][d], cf[d]);
-                    knn_mark32<NP>(df, T[q], 1u << t, mb[q]);
+                    for (int d = 0; d < NPA; d += 2) {
+                        unsigned long long dd;
+                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(qf2[q][d / 2]), "l"(cf2[d / 2]));
+                        asm("mov.b64 {%0,%1}, %2;" : "=f"(df[d]), "=f"(df[d + 1]) : "l"(dd));
+                    }
+                    float dn[NP];
+                    #pragma unroll
+                    for (int d = 0; d < NP; d++) dn[d] = df[d];
+                    knn_mark32<NP>(dn, T[q], 1u << t, mb[q]);
                 }
             }
             #pragma unroll
@@ -265,7 +272,10 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         #pragma unroll
         for (int q = 0; q < Q; q++)
             #pragma unroll
-            for (int d = 0; d < NP; d++) qf[q][d] = __double2float_rn(qc[q][d]);
+            for (int d = 0; d < NPA; d += 2) {
+                const float a = __double2float_rn(qc[q][d]), b = (d + 1 < NP) ? __double2float_rn(qc[q][d + 1]) : 0.f;
+                asm("mov.b64 %0, {%1,%2};" : "=l"(qf2[q][d / 2]) : "f"(a), "f"(b));
+            }
     };
 
     unsigned long long nvis = 0;
