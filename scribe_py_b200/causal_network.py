@@ -24,6 +24,38 @@ from . import distributed as _dist
 __all__ = ["causal_model"]
 
 
+class _PairDelayJobs:
+    """Job table of rdi(): every ordered pair x delay, delay-major.  Only the slices a rank asks for are materialised
+    (`jobs[lo:hi]` -> JOB_DTYPE array), so the per-rank host work of a sharded call is proportional to its slab."""
+
+    def __init__(self, src, tgt, delays):
+        self.src, self.tgt, self.delays = src, tgt, np.asarray(list(delays), dtype=np.int32)
+        self.per = len(src)
+        self._last = None                                # (lo, hi, table): a repeated request (same slab every step) is free
+
+    def __len__(self):
+        return self.per * len(self.delays)
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice):
+            raise TypeError("job tables are sliced, not indexed")
+        lo, hi, step = key.indices(len(self))
+        assert step == 1
+        if self._last is not None and self._last[0] == lo and self._last[1] == hi:
+            return self._last[2]
+        jobs = np.zeros(max(hi - lo, 0), dtype=_lib.JOB_DTYPE)
+        per = max(self.per, 1)
+        for i in range(lo // per, len(self.delays)):                 # one contiguous copy per delay the slab touches
+            a, b = max(lo, i * per), min(hi, (i + 1) * per)
+            if a >= b:
+                break
+            o = slice(a - lo, b - lo)
+            jobs["src"][o] = self.src[a - i * per:b - i * per]; jobs["dst"][o] = self.tgt[a - i * per:b - i * per]
+            jobs["delay"][o] = self.delays[i]
+        self._last = (lo, hi, jobs)
+        return jobs
+
+
 class causal_model(object):
     """Holds gene expression (genes x cells, single-run index GENE_ID or MultiIndex (GENE_ID, RUN_ID)) and
     computes pairwise RDI / cRDI scores on the GPU."""
@@ -183,10 +215,7 @@ class causal_model(object):
         off = tgt != src
         tgt, src = tgt[off], src[off]
         per = len(tgt)
-        jobs = np.zeros(per * len(delays), dtype=_lib.JOB_DTYPE)
-        for i, d in enumerate(delays):
-            sl = slice(i * per, (i + 1) * per)
-            jobs["src"][sl] = src; jobs["dst"][sl] = tgt; jobs["delay"][sl] = int(d)
+        jobs = _PairDelayJobs(src, tgt, delays)
         scales = None
         if differential_mode:
             st = self._lag_std(E, run_off, delays)
@@ -286,9 +315,11 @@ class causal_model(object):
         return self.crdi_results
 
     # ------------------------------------------------------------------ reductions over the RDI matrices
-    @staticmethod
-    def __square(frame, node_ids, dtype=np.float64):
+    def __square(self, frame, node_ids, dtype=np.float64):
         """frame.loc[node_ids, node_ids] as an array, without the label lookup when the frame is already in node order."""
+        ix = getattr(self, "_ix_cache", None)
+        if ix is not None and frame.index is ix[1] and frame.columns is ix[1] and ix[0] == node_ids:   # built by _frame()
+            return frame.to_numpy(dtype=dtype)
         if frame.shape == (len(node_ids), len(node_ids)) and list(frame.index) == node_ids and list(frame.columns) == node_ids:
             return frame.to_numpy(dtype=dtype)
         return frame.loc[node_ids, node_ids].to_numpy(dtype=dtype)
