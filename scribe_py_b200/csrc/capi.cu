@@ -584,8 +584,10 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         std::vector<int> colidx;          // D per job
         int n_max = 0;
         int64_t end = pos;
+        // per-point workspace: cumi weights; generic path eps/counts/sums; strip images only where the strip kernels run
+        const bool strips = o->path == SCRIBE_PATH_STRIP || (o->path == SCRIBE_PATH_AUTO && h->sweep_v1 && o->estimator == SCRIBE_EST_CUMI);
         size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0)
-                         + (o->path == SCRIBE_PATH_AUTO || o->path == SCRIBE_PATH_STRIP ? (size_t)(std::max(D, 8) * 8 + 8) : 0);
+                         + (strips ? (size_t)(std::max(D, 8) * 8 + 8) : 0);
         while (end < n_jobs && jobs[end].n_cond == L && (end - pos) < 262144) {
             const scribe_job& jb = jobs[end];
             if (jb.src < 0 || jb.src >= h->n_genes || jb.dst < 0 || jb.dst >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
@@ -702,7 +704,8 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
     }
     double* out_dev = out;
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / (12 * N * 8))));   // columns + strip images
+    const bool strips = o->path == SCRIBE_PATH_STRIP;                                                 // 3 compacted columns + order (+ strip images)
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / ((strips ? 12 : 4) * N * 8))));
     h->idx32a.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->idx32b.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->neff.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
