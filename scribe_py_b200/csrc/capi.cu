@@ -56,7 +56,8 @@ struct scribe_handle {
     // workspaces
     DevBuf psi; int psi_n = 0;
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
-    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips;
+    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, xsorted, permE, sortedE;
+    bool sortE_valid = false;             // permE / sortedE describe the uploaded expression matrix
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
@@ -162,6 +163,7 @@ SweepFn pick_sweepw_k(int kcap) {
 SweepFn pick_sweepw(int dx, int dy, int dz, int kcap, bool weighted) {
     if (dx != 1 || dy != 1) return nullptr;
     switch (dz) {
+        case 0: return weighted ? nullptr : pick_sweepw_k<0, false>(kcap);      // mi(x, y): sorted by y, x marginal by rank
         case 1: return weighted ? pick_sweepw_k<1, true>(kcap) : pick_sweepw_k<1, false>(kcap);
         case 2: return weighted ? pick_sweepw_k<2, true>(kcap) : pick_sweepw_k<2, false>(kcap);
         case 3: return weighted ? pick_sweepw_k<3, true>(kcap) : pick_sweepw_k<3, false>(kcap);
@@ -209,8 +211,12 @@ KdeSweepFn pick_kde_sweep(int dp) {
 // Will run_jobs take the sorted-sweep kernels for this configuration?  (callers must then provide JobDesc.perm
 // or pre-sorted columns)
 bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
-    if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) return false;
     const int kcap = (o->k + 1 <= 6) ? 6 : ((o->k + 1 <= 16) ? 16 : 0);
+    if (o->estimator == SCRIBE_EST_MI) {                   // windowed sweep only (sorted by y; JobDesc.xsorted for the x marginal)
+        if (!kcap || !pick_sweepw(dx, dy, 0, kcap, false)) return false;
+        return o->path == SCRIBE_PATH_SWEEP || (o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N);
+    }
+    if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) return false;
     if (!kcap || !pick_sweep(dx, dy, dz, kcap, false)) return false;
     if (o->path == SCRIBE_PATH_SWEEP || o->path == SCRIBE_PATH_STRIP) return true;
     return o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N;
@@ -295,7 +301,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
         use_strip2 = dz == 1 && !h->no_strip2 && (o->path == SCRIBE_PATH_STRIP || n_max >= 4096);
         sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
-        if (!h->sweep_v1) { sweep = pick_sweepw(dx, dy, dz, kcap, weighted); windowed = true; }
+        if (!h->sweep_v1 || dz == 0) { sweep = pick_sweepw(dx, dy, dz, kcap, weighted); windowed = true; }
     }
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
@@ -519,8 +525,14 @@ void single_job(scribe_handle* h, const double* x, const double* y, const double
     h->out.ensure(sizeof(double));
     bool dom = false;
     bool ordered = false;
-    if (want_sweep(o, dx, dy, dz, (int)n)) {                 // argsort of the last conditioning column
+    if (want_sweep(o, dx, dy, dz, (int)n)) {                 // argsort of the last column (last conditioning column; y for mi)
         h->perm.ensure(sizeof(int32_t) * n);
+        if (dz == 0) {                                       // mi: x in ascending order for its marginal count
+            sort_segments(h, hj[0].col[0], 1, n, std::vector<int>{(int)n}, h->perm.as<int32_t>());
+            h->xsorted.ensure(sizeof(double) * n);
+            CU(cudaMemcpyAsync(h->xsorted.p, h->keys_out.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+            hj[0].xsorted = h->xsorted.as<double>();
+        }
         sort_segments(h, hj[0].col[D - 1], 1, n, std::vector<int>{(int)n}, h->perm.as<int32_t>());
         hj[0].perm = h->perm.as<int32_t>();
         ordered = true;
@@ -759,6 +771,14 @@ void mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n
     begin_call(h);
     h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1));
     const int64_t N = h->n_cells;
+    const bool ordered = want_sweep(o, 1, 1, 0, (int)N) && (int64_t)h->n_genes * N < ((int64_t)1 << 31);
+    if (ordered && !h->sortE_valid) {                    // every gene's row: argsort + sorted values, once per upload
+        h->permE.ensure(sizeof(int32_t) * h->n_genes * N);
+        h->sortedE.ensure(sizeof(double) * h->n_genes * N);
+        sort_segments(h, h->E.as<double>(), (int)h->n_genes, N, std::vector<int>((size_t)h->n_genes, (int)N), h->permE.as<int32_t>());
+        CU(cudaMemcpyAsync(h->sortedE.p, h->keys_out.p, sizeof(double) * h->n_genes * N, cudaMemcpyDeviceToDevice, h->stream));
+        h->sortE_valid = true;
+    }
     for (int64_t pos = 0; pos < n_jobs; pos += 262144) {
         const int64_t nj = std::min<int64_t>(262144, n_jobs - pos);
         std::vector<JobDesc> hj(nj);
@@ -769,9 +789,10 @@ void mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n
             hj[j].col[0] = h->E.as<double>() + (size_t)a * N;
             hj[j].col[1] = h->E.as<double>() + (size_t)b * N;
             hj[j].n = (int)N;
+            if (ordered) { hj[j].perm = h->permE.as<int32_t>() + (size_t)b * N; hj[j].xsorted = h->sortedE.as<double>() + (size_t)a * N; }
             h->st.point_pairs += N * N;
         }
-        run_jobs(h, hj, (int)N, 1, 1, 0, o, h->out.as<double>() + pos, false, nullptr, nullptr);
+        run_jobs(h, hj, (int)N, 1, 1, 0, o, h->out.as<double>() + pos, false, nullptr, nullptr, ordered);
     }
     if (n_jobs > 0) {
         CU(cudaMemcpyAsync(out, h->out.p, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, h->stream));
@@ -832,7 +853,7 @@ void scribe_destroy(scribe_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
                       &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
-                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips})
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->xsorted, &h->permE, &h->sortedE})
         b->release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
     cudaStreamDestroy(h->stream);
@@ -886,7 +907,7 @@ int scribe_upload_matrix(scribe_handle* h, const double* E, int64_t n_genes, int
         CU(cudaMemcpyAsync(h->run_off_d.p, ro.data(), sizeof(int64_t) * ro.size(), cudaMemcpyHostToDevice, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         h->st.h2d_bytes = sizeof(double) * n_genes * n_cells + sizeof(int64_t) * ro.size();
-        h->n_genes = n_genes; h->n_cells = n_cells; h->run_off = ro;
+        h->n_genes = n_genes; h->n_cells = n_cells; h->run_off = ro; h->sortE_valid = false;
         end_call(h);
     });
 }

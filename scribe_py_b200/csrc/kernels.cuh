@@ -37,6 +37,7 @@ struct JobDesc {
     int32_t n;                // points
     int32_t pad;
     double absmax;            // windowed sweep: largest |coordinate| of the job, written on the device by job_absmax_kernel
+    const double* xsorted;    // windowed sweep for mi (no conditioning column): col[0] in ascending order (marginal count of x)
 };
 
 struct PointOut {             // optional per-point outputs (debug entry point, generic path, kNN-only mode)

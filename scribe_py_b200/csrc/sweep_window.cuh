@@ -61,8 +61,11 @@ job_absmax_kernel(JobDesc* __restrict__ jobs, int D)
 template <int NP>
 __device__ __forceinline__ void knn_mark32(const float (&df)[NP], float T, unsigned bit, unsigned& mask)
 {
-    static_assert(NP >= 2 && NP <= 4, "2..4 non-key coordinates");
-    if (NP == 2)
+    static_assert(NP >= 1 && NP <= 4, "1..4 non-key coordinates");
+    if (NP == 1)
+        asm("{\n .reg .pred p;\n .reg .f32 a0;\n abs.f32 a0,%1;\n setp.leu.f32 p, a0, %2;\n @p or.b32 %0,%0,%3;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(T), "r"(bit));
+    else if (NP == 2)
         asm("{\n .reg .pred p;\n .reg .f32 a0,a1;\n abs.f32 a0,%1; abs.f32 a1,%2;\n"
             " setp.leu.f32 p, a0, %3;\n setp.leu.and.f32 p, a1, %3, p;\n @p or.b32 %0,%0,%4;\n}"
             : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(T), "r"(bit));
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(SWEEP_TPB, SWEEPW_MIN_CTAS)
 ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                   double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
-    static_assert(DZ >= 1 && DZ <= 3, "1..3 conditioning columns");
+    static_assert(DZ >= 0 && DZ <= 3 && !(DZ == 0 && WEIGHTED), "0..3 conditioning columns; DZ = 0 is mi(x, y): sorted by y");
     constexpr int D   = 2 + DZ;
     constexpr int KEY = D - 1;
     constexpr int NP  = D - 1;                    // non-key coordinates: x, y, z_0 .. z_{DZ-2}
@@ -398,9 +401,38 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         #pragma unroll
         for (int q = 0; q < Q; q++) { lo[q] = la[q]; hi[q] = ha[q] - 1; }
     }
+    int nxm[Q];                                                    // mi: marginal count of x over ALL points (incl. self)
+    #pragma unroll
+    for (int q = 0; q < Q; q++) nxm[q] = 0;
+    if constexpr (DZ == 0) {
+        const double* __restrict__ xs = jd.xsorted;                // col[0] ascending: the ball |x_i - x_j| <= eps is a rank range
+        int la[Q], lb[Q], ha[Q], hb[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { la[q] = 0; lb[q] = n; ha[q] = 0; hb[q] = n; }
+        const int iters = 33 - __clz(n);
+        for (int it = 0; it < iters; it++) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                if (la[q] < lb[q]) {
+                    const int mid = (la[q] + lb[q]) >> 1;
+                    const double xr = xs[mid];
+                    const bool A = (xr > qc[q][0]) || (fabs(qc[q][0] - xr) <= eps[q]);
+                    if (A) lb[q] = mid; else la[q] = mid + 1;
+                }
+                if (ha[q] < hb[q]) {
+                    const int mid = (ha[q] + hb[q]) >> 1;
+                    const double xr = xs[mid];
+                    const bool B = (xr < qc[q][0]) || (fabs(qc[q][0] - xr) <= eps[q]);
+                    if (B) ha[q] = mid + 1; else hb[q] = mid;
+                }
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < Q; q++) nxm[q] = ha[q] - la[q];
+    }
     int nxyz[Q], nxz[Q], nyz[Q], nz[Q];
     #pragma unroll
-    for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = 0; nz[q] = (DZ == 1) ? hi[q] - lo[q] + 1 : 0; }
+    for (int q = 0; q < Q; q++) { nxyz[q] = nxz[q] = nyz[q] = 0; nz[q] = (DZ <= 1) ? hi[q] - lo[q] + 1 : 0; }
 
     int clo[Q], chi[Q];
     #pragma unroll
@@ -438,7 +470,9 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                 #pragma unroll
                 for (int q = Q0; q < Q; q++) {
                     ball_bit(qc[q][0] - cc[0], eps[q], bit, bx[q]);
-                    if constexpr (!WEIGHTED) {
+                    if constexpr (DZ == 0) {
+                        // mi: the key is y itself; only x is tested inside the y-window
+                    } else if constexpr (!WEIGHTED) {
                         ball_bit(qc[q][1] - cc[1], eps[q], bit, by[q]);
                         if constexpr (DZ == 2) ball_bit(qc[q][2] - cc[2], eps[q], bit, bz[q]);
                         if constexpr (DZ == 3) ball_bit2(qc[q][2] - cc[2], qc[q][3] - cc[3], eps[q], bit, bz[q]);
@@ -456,7 +490,9 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         }
         #pragma unroll
         for (int q = Q0; q < Q; q++) {
-            if (!WEIGHTED) {
+            if (DZ == 0) {
+                nxz[q] += __popc(zw[q] & mx[q]);                  // n_xy: x-ball inside the y-window
+            } else if (!WEIGHTED) {
                 unsigned z = zw[q];
                 if (DZ > 1) { z &= mz[q]; nz[q] += __popc(z); }
                 const unsigned xw = z & mx[q];
@@ -500,7 +536,10 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         if (qok[q]) {
             const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
             const int64_t o = jd.qoff + qidx[q];
-            if (WEIGHTED) {
+            if (DZ == 0) {
+                // information_estimators.py:102-107: psi(N) + psi(n_xy) - psi(n_x) - psi(n_y); slots as in the dense kernel
+                acc += psi_int(psi_tab, n) + psi_int(psi_tab, b) - psi_int(psi_tab, nxm[q] - 1) - psi_int(psi_tab, d);
+            } else if (WEIGHTED) {
                 const double wi = qw[q];
                 const double Wyz = wyz[q] - wi, Wz = wz[q] - wi;
                 acc += wi * psi_int(psi_tab, a) + wi * -psi_int(psi_tab, b) + wi * -digamma_f64(Wyz) + wi * digamma_f64(Wz);
@@ -509,7 +548,11 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                 acc += psi_int(psi_tab, a) - psi_int(psi_tab, b) - psi_int(psi_tab, c) + psi_int(psi_tab, d);
             }
             if (po.eps) po.eps[o] = eps[q];
-            if (po.cnt) { int32_t* oc = po.cnt + 4 * o; oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+            if (po.cnt) {
+                int32_t* oc = po.cnt + 4 * o;
+                if (DZ == 0) { oc[0] = b; oc[1] = nxm[q] - 1; oc[2] = d; oc[3] = n - 1; }      // n_xy, n_x, n_y, (all)
+                else         { oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
+            }
         }
     }
     #pragma unroll

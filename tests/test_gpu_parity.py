@@ -428,3 +428,51 @@ def test_windowed_sweep_vs_first_sweep_poisson(S, n):
         P = np.concatenate((x, y, z), axis=1)
         eps, cnt = o.knn_counts(P, [(0, 1, 2), (0, 2), (1, 2), (2,)], 5)
         assert np.array_equal(b["eps"], eps) and np.array_equal(b["counts"], cnt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [3, 5, 10])
+@pytest.mark.parametrize("kind", ["continuous", "ties", "poisson"])
+def test_mi_sweep_against_oracle(S, k, kind):
+    """mi on the windowed sweep (sorted by y, x marginal by rank range): eps and the three counts bit-identical to the
+    oracle and to the dense kernel, value equal to the dense kernel's"""
+    rng = np.random.default_rng(31 * k + len(kind))
+    n = 1237
+    if kind == "poisson":
+        x = rng.poisson(2.0, (n, 1)).astype(float); y = (x + rng.poisson(1.0, (n, 1))).astype(float)
+    else:
+        x = rng.standard_normal((n, 1)); y = 0.6 * x + rng.standard_normal((n, 1))
+        if kind == "ties":
+            x = np.round(x, 1); y = np.round(y, 1)
+    P = np.concatenate((x, y), axis=1)
+    eps, cnt = o.knn_counts(P, [(0, 1), (0,), (1,)], k)
+    a = S.information_estimators.ksg_debug("mi", x, y, k=k, path="dense")
+    b = S.information_estimators.ksg_debug("mi", x, y, k=k, path="sweep")
+    assert np.array_equal(a["eps"], eps) and np.array_equal(b["eps"], eps)
+    assert np.array_equal(np.asarray(a["counts"])[:3], cnt) and np.array_equal(np.asarray(b["counts"])[:3], cnt)
+    h = S._lib.default_handle()
+    xs, ys = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    v_d = h.estimate(xs, ys, None, S._lib.make_opts(S._lib.EST_MI, k, path=S._lib.PATH_DENSE))
+    v_s = h.estimate(xs, ys, None, S._lib.make_opts(S._lib.EST_MI, k, path=S._lib.PATH_SWEEP))
+    assert abs(v_d - v_s) < 1e-12 and close(v_s, o.mi(x, y, k=k), TOL_EXACT)
+
+
+@pytest.mark.gpu
+def test_mi_network_sweep_equals_dense(S):
+    """scribe_mi_jobs through the sweep (per-gene argsort + sorted rows cached per upload) == dense kernel, every pair"""
+    rng = np.random.default_rng(5)
+    G, T = 9, 700
+    E = rng.standard_normal((G, T)); E[3] = 0.7 * E[1] + 0.3 * rng.standard_normal(T); E[5] = np.round(E[5], 1)
+    h = S._lib.default_handle()
+    src, dst = np.nonzero(~np.eye(G, dtype=bool))
+    src, dst = src.astype(np.int32), dst.astype(np.int32)
+    h.upload_matrix(E)
+    v_s = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_SWEEP))
+    v_d = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_DENSE))
+    assert np.abs(v_s - v_d).max() < 1e-12
+    ref = np.array([o.mi(E[a][:, None], E[b][:, None]) for a, b in zip(src[:12], dst[:12])])
+    assert np.abs(v_s[:12] - ref).max() < TOL_EXACT
+    h.upload_matrix(E[::-1].copy())                       # a new upload must invalidate the cached order
+    v2 = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_SWEEP))
+    v2d = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_DENSE))
+    assert np.abs(v2 - v2d).max() < 1e-12 and np.abs(v2 - v_s).max() > 1e-6

@@ -33,6 +33,25 @@ def run(G, T, delays, est, reps=2):
           % (os.environ.get("SCRIBE_B200_Q", "auto"), est, G, T, len(jobs), best["estimator_ms"], best["total_ms"],
              len(jobs) / (best["total_ms"] * 1e-3), pairs / (best["estimator_ms"] * 1e-3), cps, float(np.nansum(v))), flush=True)
 
+def run_mi(G, T, reps=2):
+    """all ordered pairs of the batched MI network (other_estimators.mi -> scribe_mi_jobs)"""
+    E = recipes.rdi_synthetic(G, T, 2) if T <= 4000 else np.random.default_rng(0).standard_normal((G, T)).cumsum(axis=1) * 0.05 + np.random.default_rng(1).standard_normal((G, T))
+    h = _lib.default_handle()
+    h.upload_matrix(E)
+    src, dst = np.nonzero(~np.eye(G, dtype=bool))
+    opts = _lib.make_opts(_lib.EST_MI, 5)
+    best = None
+    for _ in range(reps + 1):
+        v = h.mi_jobs(src.astype(np.int32), dst.astype(np.int32), opts)
+        st = h.stats()
+        if best is None or st["estimator_ms"] < best["estimator_ms"]:
+            best = st
+    print("mi path=%s G=%d T=%d jobs=%d est_ms=%.2f total_ms=%.2f evals/s=%.0f visited=%.3f checksum=%.12f"
+          % (os.environ.get("SCRIBE_B200_PATH", "auto"), G, T, len(src), best["estimator_ms"], best["total_ms"],
+             len(src) / (best["total_ms"] * 1e-3), (best["visited_knn"] + best["visited_count"]) / (2.0 * best["point_pairs"]),
+             float(np.nansum(v))), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "cmi"
     if what == "cmi":
@@ -50,6 +69,9 @@ if __name__ == "__main__":
         run(24, 20000, [1], _lib.EST_CMI, reps=1)
     elif what == "c5one":
         run(16, 20000, [1], _lib.EST_CUMI, reps=1)
+    elif what == "mi":
+        for T, G in ((2000, 60), (20000, 16)):
+            run_mi(G, T, reps=1)
     elif what == "matrix":
         for T, G in ((1000, 60), (2000, 60), (5000, 30), (10000, 20), (20000, 16)):
             for est in (_lib.EST_CMI, _lib.EST_CUMI):
