@@ -7,6 +7,7 @@
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -565,6 +566,18 @@ struct ColKeyHash {
     }
 };
 
+// SCRIBE_B200_TRACE=1: host wall-clock per phase of a call, to stderr (diagnostics only)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t;
+    Trace() : on(std::getenv("SCRIBE_B200_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[scribe trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const scribe_opts* o, int differential,
                  const double* scales, double* out, bool out_is_device)
 {
@@ -573,6 +586,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
     if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
     if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !out))) fail(SCRIBE_E_ARG, "NULL jobs/out");
     begin_call(h);
+    Trace tr;
     const int n_runs = (int)h->run_off.size() - 1;
     // jobs are processed in chunks of equal conditioning-set size (equal joint dimension)
     int64_t pos = 0;
@@ -587,19 +601,36 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         if (L < 0 || L > SCRIBE_MAX_COND) fail(SCRIBE_E_ARG, "n_cond out of range");
         const int dz = L + 1, D = dz + 2;
         // chunk: same n_cond, bounded workspace
-        std::unordered_map<ColKey, int, ColKeyHash> colmap;
-        colmap.reserve(8192);
+        // distinct lagged columns of the chunk: open-addressing table over `specs` (no per-entry allocation; the loop below is
+        // on the critical path of every call -- the GPU is idle while it runs)
+        std::vector<int32_t> table(1u << 14, -1);
+        std::vector<uint64_t> spec_scale;                                                     // scale bits per spec (part of the key)
         ColKey last_key[2 + SCRIBE_MAX_COND + 1]; int last_id[2 + SCRIBE_MAX_COND + 1];     // per-role one-entry cache: jobs arrive
         for (auto& v : last_id) v = -1;                                                      // target-major, so y/z columns repeat
         std::vector<ColSpec> specs;
-        std::vector<JobDesc> hj;
+        std::vector<int32_t> n_of;        // samples per job
         std::vector<int> colidx;          // D per job
+        const int64_t room = std::min<int64_t>(n_jobs - pos, 262144);
+        n_of.reserve(room); colidx.reserve(room * D); specs.reserve(4096); spec_scale.reserve(4096);
+        auto rehash = [&]() {
+            std::vector<int32_t> bigger(table.size() * 4, -1);
+            const size_t mask = bigger.size() - 1;
+            for (size_t id = 0; id < specs.size(); id++) {
+                const ColSpec& sp = specs[id];
+                size_t slot = ColKeyHash{}(ColKey{sp.gene, sp.shift, sp.tau, sp.diff, spec_scale[id]}) & mask;
+                while (bigger[slot] >= 0) slot = (slot + 1) & mask;
+                bigger[slot] = (int32_t)id;
+            }
+            table.swap(bigger);
+        };
         int n_max = 0;
         int64_t end = pos;
         // per-point workspace: cumi weights; generic path eps/counts/sums; strip images only where the strip kernels run
         const bool strips = o->path == SCRIBE_PATH_STRIP || (o->path == SCRIBE_PATH_AUTO && h->sweep_v1 && o->estimator == SCRIBE_EST_CUMI);
         size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0)
                          + (strips ? (size_t)(std::max(D, 8) * 8 + 8) : 0);
+        int tau_cached = -1; int64_t n_cached = 0;
+        int64_t pairs = 0;
         while (end < n_jobs && jobs[end].n_cond == L && (end - pos) < 262144) {
             const scribe_job& jb = jobs[end];
             if (jb.src < 0 || jb.src >= h->n_genes || jb.dst < 0 || jb.dst >= h->n_genes) fail(SCRIBE_E_ARG, "gene index out of range");
@@ -610,7 +641,8 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
                 if (jb.cond_delay[c] < 1) fail(SCRIBE_E_ARG, "conditioning delay must be >= 1");
                 tau = std::max(tau, jb.cond_delay[c]);
             }
-            const int64_t n = n_for_tau(tau);
+            if (tau != tau_cached) { n_cached = n_for_tau(tau); tau_cached = tau; }
+            const int64_t n = n_cached;
             if (n < 1) fail(SCRIBE_E_LENGTH, "delay leaves no samples");
             if (n > 2000000) fail(SCRIBE_E_ARG, "too many cells");
             const int64_t new_nmax = std::max<int64_t>(n_max, n);
@@ -623,13 +655,21 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
                 ColKey key{gene, shift, tau, diff, 0};
                 std::memcpy(&key.scale_bits, &sc, 8);
                 if (last_id[role] >= 0 && last_key[role] == key) return last_id[role];
-                int id;
-                auto it = colmap.find(key);
-                if (it != colmap.end()) id = it->second;
-                else {
+                const size_t mask = table.size() - 1;
+                size_t slot = ColKeyHash{}(key) & mask;
+                int id = -1;
+                while (table[slot] >= 0) {
+                    const int c = table[slot];
+                    const ColSpec& sp = specs[c];
+                    if (sp.gene == gene && sp.shift == shift && sp.tau == tau && sp.diff == diff && spec_scale[c] == key.scale_bits) { id = c; break; }
+                    slot = (slot + 1) & mask;
+                }
+                if (id < 0) {
                     id = (int)specs.size();
                     specs.push_back(ColSpec{gene, shift, tau, diff, sc});
-                    colmap.emplace(key, id);
+                    spec_scale.push_back(key.scale_bits);
+                    table[slot] = id;
+                    if (specs.size() * 2 > table.size()) rehash();
                 }
                 last_key[role] = key; last_id[role] = id;
                 return id;
@@ -639,13 +679,16 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             for (int c = L - 1; c >= 0; c--)                                         // z: cond[L-1] .. cond[0], then dst's past (cn:273-278)
                 colidx.push_back(get(2 + c, jb.cond_gene[c], tau - jb.cond_delay[c], 0, sz));
             colidx.push_back(get(2 + SCRIBE_MAX_COND, jb.dst, tau - 1, 0, sz));      //     (cn:149,:267)
-            JobDesc jd; std::memset(&jd, 0, sizeof(jd)); jd.n = (int)n;
-            hj.push_back(jd);
-            h->st.point_pairs += n * n;
+            n_of.push_back((int32_t)n);
+            pairs += n * n;
             end++;
         }
+        h->st.point_pairs += pairs;
+        std::vector<JobDesc> hj((size_t)(end - pos));                                // value-initialised: all fields zero
+        for (size_t j = 0; j < hj.size(); j++) hj[j].n = n_of[j];
         const int64_t nj = end - pos;
         const int64_t stride = n_max;
+        tr.lap("job loop (host)");
         h->cols.ensure(sizeof(double) * specs.size() * stride);
         h->specs.ensure(sizeof(ColSpec) * specs.size());
         CU(cudaMemcpyAsync(h->specs.p, specs.data(), sizeof(ColSpec) * specs.size(), cudaMemcpyHostToDevice, h->stream));
@@ -663,6 +706,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         }
         for (int64_t j = 0; j < nj; j++)
             for (int c = 0; c < D; c++) hj[j].col[c] = h->cols.as<double>() + (size_t)colidx[j * D + c] * stride;
+        tr.lap("gather launch + col pointers");
         bool ordered = false;
         if (want_sweep(o, 1, 1, dz, n_max)) {
             // one argsort per distinct key column (the target's own past, last z column): shared by every source gene
@@ -687,7 +731,9 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             for (int64_t j = 0; j < nj; j++) hj[j].perm = h->perm.as<int32_t>() + (size_t)slot[colidx[j * D + D - 1]] * stride;
             ordered = true;
         }
+        tr.lap("key select + argsort");
         run_jobs(h, hj, n_max, 1, 1, dz, o, out_dev + pos, false, nullptr, nullptr, ordered);
+        tr.lap("run_jobs");
         pos = end;
     }
     if (!out_is_device && n_jobs > 0) {
@@ -695,6 +741,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         h->st.d2h_bytes += sizeof(double) * n_jobs;
     }
     end_call(h);
+    tr.lap("result copy + end");
 }
 
 void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs, int drop_zero,
