@@ -167,3 +167,27 @@ def test_load_anndata_branches_as_runs(S):
     m2 = S.load_anndata(ad2)
     assert m2.expression.shape == (G, n) and list(m2.run_ids) == [0]
     assert np.array_equal(m2._dense()[1], X.T)
+
+
+def test_pair_delay_job_table_slices():
+    """the lazily materialised rdi job table: any slab equals the same slice of the full delay-major table"""
+    from scribe_py_b200.causal_network import _PairDelayJobs
+    G = 7
+    tgt, src = np.meshgrid(np.arange(G, dtype=np.int32), np.arange(G, dtype=np.int32), indexing="ij")
+    off = tgt != src
+    tgt, src = tgt[off], src[off]
+    delays = [1, 5, 10]
+    t = _PairDelayJobs(src, tgt, delays)
+    per = G * (G - 1)
+    assert len(t) == per * len(delays)
+    full = t[0:len(t)]
+    assert (full["src"] == np.tile(src, 3)).all() and (full["dst"] == np.tile(tgt, 3)).all()
+    assert (full["delay"] == np.repeat(delays, per)).all() and (full["n_cond"] == 0).all()
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        lo, hi = sorted(rng.integers(0, len(t) + 1, 2))
+        part = t[lo:hi]
+        assert len(part) == hi - lo and (part == full[lo:hi]).all()
+    assert t[5:9] is t[5:9]                                  # a repeated slab request is served from the one-entry cache
+    with pytest.raises(TypeError):
+        t[3]
