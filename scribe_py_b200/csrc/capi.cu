@@ -57,11 +57,12 @@ struct scribe_handle {
     // workspaces
     DevBuf psi; int psi_n = 0;
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
-    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, xsorted, permE, sortedE;
+    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, xsorted, permE, sortedE, rawjobs;
     bool sortE_valid = false;             // permE / sortedE describe the uploaded expression matrix
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
     int force_q = 0;                      // SCRIBE_B200_Q: override queries per thread (tuning)
+    int no_fast_rdi = 0;                  // SCRIBE_B200_NO_FAST_RDI=1: always take the generic job loop of scribe_lagged_jobs
     int sweep_v1 = 0;                     // SCRIBE_B200_SWEEP_V1=1: first sweep form (FP64 scan in both passes) for unweighted jobs too
     int no_strip2 = 0;                    // SCRIBE_B200_NO_STRIP2=1: use the first strip form also for dz = 1 (tuning)
 };
@@ -269,10 +270,13 @@ struct DebugPtrs { double* eps = nullptr; int32_t* cnt = nullptr; double* wsum =
 // dbg (optional, single-chunk only): host pointers that receive the per-point quantities of job 0..n-1.
 void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int dy, int dz,
               const scribe_opts* o, double* out_dev, bool n_on_device, const DebugPtrs* dbg, bool* domain_error,
-              bool have_order = false)
+              bool have_order = false, int64_t nj_dev = -1)
 {
-    const int64_t nj = (int64_t)hj.size();
+    // nj_dev >= 0: the descriptors of nj_dev jobs (qoff included) were built in h->jobs on the device; `hj` is not used
+    const bool host_desc = nj_dev < 0;
+    const int64_t nj = host_desc ? (int64_t)hj.size() : nj_dev;
     if (nj == 0) return;
+    if (!host_desc && (!n_on_device || dbg)) fail(SCRIBE_E_STATE, "device-built descriptors: internal misuse");
     const int est = o->estimator;
     const int D = dx + dy + dz;
     if (dx < 1 || dy < 1 || dz < 0 || D > SCRIBE_MAX_DIM) fail(SCRIBE_E_ARG, "unsupported dimensions (need dx,dy >= 1, dx+dy+dz <= 16)");
@@ -280,7 +284,8 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     if ((est == SCRIBE_EST_CMI || est == SCRIBE_EST_CUMI) && dz < 1) fail(SCRIBE_E_ARG, "cmi/cumi need a conditioning variable");
     const bool weighted = est >= SCRIBE_EST_UMI;
     const bool euclid = est == SCRIBE_EST_UMI;
-    if (weighted && n_on_device) fail(SCRIBE_E_ARG, "uniformised estimators are not available on the coupling path");
+    if (weighted && n_on_device && host_desc) fail(SCRIBE_E_ARG, "uniformised estimators are not available on the coupling path");
+    if (weighted && !host_desc && o->density != SCRIBE_DENSITY_KDE) fail(SCRIBE_E_STATE, "device-built descriptors need the KDE weights");
     ensure_psi(h, n_max);
 
     const int k = o->k;
@@ -314,7 +319,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         visited = h->visited.as<unsigned long long>();
     }
 
-    for (int64_t j = 0; j < nj; j++) hj[j].qoff = j * (int64_t)n_max;
+    if (host_desc) for (int64_t j = 0; j < nj; j++) hj[j].qoff = j * (int64_t)n_max;
     const int bpj_f = (n_max + TPB * q - 1) / (TPB * q);       // CTAs per job, fused
     const int bpj_1 = (n_max + TPB - 1) / TPB;                  // CTAs per job, one query per thread
     const int bpj_kde = (n_max + TPB * 2 - 1) / (TPB * 2);
@@ -382,9 +387,15 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         CU(cudaGetLastError());
         h->st.kernel_launches++;
         // point every job at its weights
-        for (int64_t j = 0; j < nj; j++) hj[j].w = u + hj[j].qoff;
-        CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        if (host_desc) {
+            for (int64_t j = 0; j < nj; j++) hj[j].w = u + hj[j].qoff;
+            CU(cudaMemcpyAsync(dj, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        } else {
+            set_weight_ptr_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, h->stream>>>(dj, nj, u);
+            CU(cudaGetLastError());
+            h->st.kernel_launches++;
+        }
     }
 
     // ---- estimator -----------------------------------------------------------------------------------
@@ -469,7 +480,7 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         unsigned long long v[3] = {0, 0, 0};
         CU(cudaMemcpy(v, h->visited.p, sizeof(v), cudaMemcpyDeviceToHost));
         h->st.visited_knn += (int64_t)v[0]; h->st.visited_count += (int64_t)v[1]; h->st.visited_kde += (int64_t)v[2];
-        if (weighted && v[2] == 0) for (int64_t j = 0; j < nj; j++) h->st.visited_kde += (int64_t)hj[j].n * hj[j].n;
+        if (weighted && v[2] == 0 && host_desc) for (int64_t j = 0; j < nj; j++) h->st.visited_kde += (int64_t)hj[j].n * hj[j].n;
     } else if (!n_on_device) {
         for (int64_t j = 0; j < nj; j++) {
             const int64_t nn = (int64_t)hj[j].n * hj[j].n;
@@ -566,6 +577,8 @@ struct ColKeyHash {
     }
 };
 
+static_assert(sizeof(RawJob) == sizeof(scribe_job), "RawJob mirrors scribe_job");
+
 // SCRIBE_B200_TRACE=1: host wall-clock per phase of a call, to stderr (diagnostics only)
 struct Trace {
     bool on; std::chrono::steady_clock::time_point t;
@@ -595,6 +608,106 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
 
     auto n_for_tau = [&](int tau) { int64_t n = 0; for (int r = 0; r < n_runs; r++) { int64_t T = h->run_off[r + 1] - h->run_off[r]; if (T > tau) n += T - tau; } return n; };
+
+    // ---- plain RDI (no conditioning set, no per-job scaling, at most 8 distinct delays, most genes in use): the lagged
+    // columns of EVERY gene and delay are laid out by formula, gathered and sorted once per call, and the descriptors are
+    // built on the device from the caller's job table -- no per-job host work beyond validation.
+    const bool weighted_knn = o->estimator == SCRIBE_EST_CUMI && o->density != SCRIBE_DENSITY_KDE;
+    if (n_jobs > 0 && !scales && !weighted_knn && !h->no_fast_rdi) {
+        RdiLayout lay; lay.n_delays = 0;
+        bool eligible = true;
+        const int64_t G = h->n_genes;
+        std::vector<int64_t> per_delay(8, 0);
+        for (int64_t j = 0; j < n_jobs && eligible; j++) {
+            const scribe_job& jb = jobs[j];
+            if (jb.n_cond != 0) { eligible = false; break; }
+            if (jb.src < 0 || jb.src >= G || jb.dst < 0 || jb.dst >= G) fail(SCRIBE_E_ARG, "gene index out of range");
+            if (jb.delay < 1) fail(SCRIBE_E_ARG, "delay must be >= 1");
+            int di = -1;
+            for (int t = 0; t < lay.n_delays; t++) if (lay.delays[t] == jb.delay) { di = t; break; }
+            if (di < 0) {
+                if (lay.n_delays == 8) { eligible = false; break; }
+                di = lay.n_delays++; lay.delays[di] = jb.delay;
+            }
+            per_delay[di]++;
+        }
+        int64_t n_max = 0;
+        if (eligible) {
+            for (int t = 0; t < lay.n_delays; t++) {
+                const int64_t n = n_for_tau(lay.delays[t]);
+                if (n < 1) fail(SCRIBE_E_LENGTH, "delay leaves no samples");
+                if (n > 2000000) fail(SCRIBE_E_ARG, "too many cells");
+                lay.n_of[t] = (int32_t)n; n_max = std::max(n_max, n);
+            }
+            for (int t = lay.n_delays; t < 8; t++) { lay.delays[t] = 0; lay.n_of[t] = 0; }
+        }
+        const int64_t ncols = 3 * G * lay.n_delays, nk = G * lay.n_delays;
+        if (eligible && (n_jobs < nk || (size_t)ncols * n_max * 8 > h->ws_budget / 2 || nk * n_max >= ((int64_t)1 << 31))) eligible = false;
+        if (eligible) {
+            const int64_t stride = n_max;
+            std::vector<ColSpec> specs((size_t)ncols);
+            for (int t = 0; t < lay.n_delays; t++)
+                for (int64_t g = 0; g < G; g++) {
+                    const int d = lay.delays[t];
+                    ColSpec* sp = &specs[(size_t)(t * G + g) * 3];
+                    sp[0] = ColSpec{(int32_t)g, 0, d, 0, 1.0};                                   // x   (cn:147)
+                    sp[1] = ColSpec{(int32_t)g, d, d, differential ? 1 : 0, 1.0};              // y   (cn:151-153)
+                    sp[2] = ColSpec{(int32_t)g, d - 1, d, 0, 1.0};                              // z   (cn:149)
+                }
+            h->cols.ensure(sizeof(double) * ncols * stride);
+            h->specs.ensure(sizeof(ColSpec) * ncols);
+            CU(cudaMemcpyAsync(h->specs.p, specs.data(), sizeof(ColSpec) * ncols, cudaMemcpyHostToDevice, h->stream));
+            h->st.h2d_bytes += sizeof(ColSpec) * ncols;
+            dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 64), 1);
+            for (int64_t c0 = 0; c0 < ncols; c0 += 65535) {
+                grid.y = (unsigned)std::min<int64_t>(65535, ncols - c0);
+                gather_lagged_kernel<<<grid, TPB, 0, h->stream>>>(h->E.as<double>(), h->n_cells, h->run_off_d.as<int64_t>(), n_runs,
+                    h->specs.as<ColSpec>() + c0, h->cols.as<double>() + c0 * stride, stride);
+                CU(cudaGetLastError());
+                h->st.kernel_launches++;
+            }
+            h->rawjobs.ensure(sizeof(scribe_job) * n_jobs);
+            CU(cudaMemcpyAsync(h->rawjobs.p, jobs, sizeof(scribe_job) * n_jobs, cudaMemcpyHostToDevice, h->stream));
+            h->st.h2d_bytes += sizeof(scribe_job) * n_jobs;
+            tr.lap("fast: validate + gather");
+            const bool ordered = want_sweep(o, 1, 1, 1, (int)n_max);
+            if (ordered) {                                    // argsort of every gene's z column (its own past), per delay
+                std::vector<int> keyspec((size_t)nk), keylen((size_t)nk);
+                for (int64_t kq = 0; kq < nk; kq++) { keyspec[kq] = (int)(kq * 3 + 2); keylen[kq] = lay.n_of[kq / G]; }
+                h->keys_in.ensure(sizeof(double) * nk * stride);
+                h->perm.ensure(sizeof(int32_t) * nk * stride);
+                h->keyspecs.ensure(sizeof(int) * nk);
+                CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
+                for (int64_t k0 = 0; k0 < nk; k0 += 65535) {
+                    dim3 g2((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min<int64_t>(65535, nk - k0));
+                    select_columns_kernel<<<g2, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
+                                                                     h->keys_in.as<double>() + (size_t)k0 * stride);
+                    CU(cudaGetLastError());
+                    h->st.kernel_launches++;
+                }
+                sort_segments(h, h->keys_in.as<double>(), (int)nk, stride, keylen, h->perm.as<int32_t>());
+            }
+            tr.lap("fast: key select + argsort");
+            for (int t = 0; t < lay.n_delays; t++) h->st.point_pairs += per_delay[t] * (int64_t)lay.n_of[t] * lay.n_of[t];
+            const bool strips = o->path == SCRIBE_PATH_STRIP || (o->path == SCRIBE_PATH_AUTO && h->sweep_v1 && o->estimator == SCRIBE_EST_CUMI);
+            const size_t per_point = (o->estimator == SCRIBE_EST_CUMI ? 8 : 0) + (o->path == SCRIBE_PATH_GENERIC ? 40 : 0) + (strips ? 72 : 0);
+            int64_t chunk = 262144;
+            if (per_point) chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)((h->ws_budget / 2) / (per_point * (size_t)n_max))));
+            std::vector<JobDesc> none;
+            for (int64_t p0 = 0; p0 < n_jobs; p0 += chunk) {
+                const int64_t nj = std::min(chunk, n_jobs - p0);
+                h->jobs.ensure(sizeof(JobDesc) * nj);
+                build_rdi_jobs_kernel<<<(unsigned)((nj + TPB - 1) / TPB), TPB, 0, h->stream>>>(
+                    reinterpret_cast<const RawJob*>(h->rawjobs.p) + p0, nj, h->jobs.as<JobDesc>(), h->cols.as<double>(), stride,
+                    ordered ? h->perm.as<int32_t>() : nullptr, (int)G, lay, n_max);
+                CU(cudaGetLastError());
+                h->st.kernel_launches++;
+                run_jobs(h, none, (int)n_max, 1, 1, 1, o, out_dev + p0, true, nullptr, nullptr, ordered, nj);
+            }
+            tr.lap("fast: run_jobs");
+            pos = n_jobs;
+        }
+    }
 
     while (pos < n_jobs) {
         const int L = jobs[pos].n_cond;
@@ -886,6 +999,7 @@ int scribe_create(int device, scribe_handle** out) {
         h->ws_budget = std::min<size_t>((size_t)8 << 30, p.totalGlobalMem / 8);
         if (const char* e = std::getenv("SCRIBE_B200_NO_STRIP2")) h->no_strip2 = std::atoi(e);
         if (const char* e = std::getenv("SCRIBE_B200_SWEEP_V1")) h->sweep_v1 = std::atoi(e);
+        if (const char* e = std::getenv("SCRIBE_B200_NO_FAST_RDI")) h->no_fast_rdi = std::atoi(e);
         if (const char* e = std::getenv("SCRIBE_B200_Q")) { int v = std::atoi(e); if (v == 1 || v == 2) h->force_q = v; }
         cudaSetDevice(prev);
         *out = h;
@@ -900,7 +1014,7 @@ void scribe_destroy(scribe_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
                       &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
-                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->xsorted, &h->permE, &h->sortedE})
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->xsorted, &h->permE, &h->sortedE, &h->rawjobs})
         b->release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
     cudaStreamDestroy(h->stream);

@@ -1768,6 +1768,47 @@ gather_lagged_kernel(const double* __restrict__ E, int64_t n_cells, const int64_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Descriptors of plain RDI jobs (no conditioning set, no per-job scaling) built on the device from the caller's job
+// table.  Column layout of the chunk: column ((di * G + gene) * 3 + role), role 0 = x (shift 0), 1 = y (shift d),
+// 2 = z (shift d-1), di = index of the job's delay in `delays`; sort order of the z columns: perm[(di * G + gene)].
+// ------------------------------------------------------------------------------------------------
+struct RdiLayout { int32_t n_delays; int32_t delays[8]; int32_t n_of[8]; };
+struct RawJob { int32_t src, dst, delay, n_cond; int32_t cond_gene[4]; int32_t cond_delay[4]; };   // == scribe_job
+
+__global__ void __launch_bounds__(TPB)
+build_rdi_jobs_kernel(const RawJob* __restrict__ raw, int64_t n_jobs, JobDesc* __restrict__ out, const double* __restrict__ cols,
+                      int64_t stride, const int32_t* __restrict__ perm, int n_genes, RdiLayout lay, int64_t n_max)
+{
+    const int64_t j = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (j >= n_jobs) return;
+    const RawJob jb = raw[j];
+    int di = 0;
+    #pragma unroll
+    for (int t = 0; t < 8; t++) if (t < lay.n_delays && lay.delays[t] == jb.delay) di = t;
+    JobDesc jd;
+    #pragma unroll
+    for (int c = 0; c < MAXD; c++) jd.col[c] = nullptr;
+    const size_t base = (size_t)di * n_genes;
+    jd.col[0] = cols + ((base + jb.src) * 3 + 0) * stride;
+    jd.col[1] = cols + ((base + jb.dst) * 3 + 1) * stride;
+    jd.col[2] = cols + ((base + jb.dst) * 3 + 2) * stride;
+    jd.w = nullptr;
+    jd.perm = perm ? perm + (base + jb.dst) * stride : nullptr;
+    jd.strip = nullptr; jd.npad = 0;
+    jd.qoff = j * n_max;
+    jd.n = lay.n_of[di]; jd.pad = 0;
+    jd.absmax = 0.0; jd.xsorted = nullptr;
+    out[j] = jd;
+}
+
+// point every job at its slice of the weight workspace (device-resident descriptors)
+__global__ void set_weight_ptr_kernel(JobDesc* __restrict__ jobs, int64_t n_jobs, const double* __restrict__ u)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) jobs[j].w = u + jobs[j].qoff;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dynamics-coupling prep (replaces Scribe.py:119-133): per job gather x = S[src], y = Y[dst], z = S[dst],
 // keep cells with (x + y) + z > 0 (float64, this association order) and compact them stably -- visiting the cells
 // in the target's z-sorted order when permS is given, so the compacted columns come out sorted for the sweep kernels

@@ -476,3 +476,39 @@ def test_mi_network_sweep_equals_dense(S):
     v2 = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_SWEEP))
     v2d = h.mi_jobs(src, dst, S._lib.make_opts(S._lib.EST_MI, 5, path=S._lib.PATH_DENSE))
     assert np.abs(v2 - v2d).max() < 1e-12 and np.abs(v2 - v_s).max() > 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("est", ["cmi", "cumi"])
+def test_rdi_fast_path_equals_generic_job_loop(S, est):
+    """scribe_lagged_jobs: the device-built descriptors of the plain-RDI fast path (full pair x delay table) give the same
+    values, bit for bit, as the generic host job loop (taken for a table with fewer jobs than gene x delay columns, for a
+    table that mixes in a conditioned job, and for multi-run input)"""
+    lib = S._lib
+    for runs in (None, [0, 300, 520]):
+        rng = np.random.default_rng(3)
+        G, T = 12, 520
+        E = np.cumsum(rng.standard_normal((G, T)), axis=1) * 0.1 + rng.standard_normal((G, T))
+        h = lib.default_handle()
+        h.upload_matrix(E, None if runs is None else np.array(runs, dtype=np.int64))
+        src, dst = np.nonzero(~np.eye(G, dtype=bool))
+        delays = [1, 3, 7]
+        jobs = np.zeros(len(src) * len(delays), dtype=lib.JOB_DTYPE)
+        for i, d in enumerate(delays):
+            sl = slice(i * len(src), (i + 1) * len(src))
+            jobs["src"][sl] = src; jobs["dst"][sl] = dst; jobs["delay"][sl] = d
+        opts = lib.make_opts(lib.EST_CUMI if est == "cumi" else lib.EST_CMI, 5, bw=0.2)
+        fast = h.lagged_jobs(jobs, opts)                                  # 396 jobs >= 12 genes x 3 delays: fast path
+        pick = np.array([0, 5, 131, 132, 200, 263, 264, 300, 395])
+        slow = h.lagged_jobs(jobs[pick], opts)                            # 9 jobs < 36 columns: generic loop
+        assert np.array_equal(fast[pick], slow)
+        mixed = jobs[pick].copy()
+        mixed = np.concatenate((mixed, mixed[:1]))
+        mixed["n_cond"][-1] = 1; mixed["cond_gene"][-1, 0] = 2; mixed["cond_delay"][-1, 0] = 2
+        got = h.lagged_jobs(mixed, opts)                                  # a conditioned job in the table: generic loop
+        assert np.array_equal(got[:-1], slow)
+        x, y, z = o.lagged_columns([E[0]] if runs is None else [E[0, a:b] for a, b in zip(runs[:-1], runs[1:])],
+                                   [E[1]] if runs is None else [E[1, a:b] for a, b in zip(runs[:-1], runs[1:])], 1, False)
+        ref = o.cumi(x, y, z, bw=0.2) if est == "cumi" else o.cmi(x, y, z)
+        j01 = int(np.nonzero((jobs["src"] == 0) & (jobs["dst"] == 1) & (jobs["delay"] == 1))[0][0])
+        assert close(fast[j01], ref, TOL_KDE if est == "cumi" else TOL_EXACT)
