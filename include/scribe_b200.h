@@ -49,12 +49,13 @@ extern "C" {
 #define SCRIBE_DENSITY_KNN 1
 
 /* kernel path selection (testing / debugging) */
-#define SCRIBE_PATH_AUTO    0  /* sorted-sweep kernels for cmi/cumi when instantiated and N >= 256 (strip kernels for
-                                  cumi with one conditioning column),
-                                  else the dense fused kernels, else the generic kernels          */
+#define SCRIBE_PATH_AUTO    0  /* windowed sorted-sweep kernel for mi/cmi/cumi (scalar x and y, <= 3 conditioning
+                                  columns, k <= 15) when N >= 256, else the dense fused kernels, else the generic
+                                  kernels                                                         */
 #define SCRIBE_PATH_GENERIC 1  /* runtime-dimension kernels (any dx,dy,dz,k within the limits)     */
 #define SCRIBE_PATH_DENSE   2  /* dense fused kernels: every query visits every candidate          */
-#define SCRIBE_PATH_SWEEP   3  /* sorted-sweep kernels regardless of N                             */
+#define SCRIBE_PATH_SWEEP   3  /* sorted-sweep kernels regardless of N (environment SCRIBE_B200_SWEEP_V1=1 selects
+                                  the first, all-FP64 form for cmi/cumi)                          */
 #define SCRIBE_PATH_STRIP   4  /* strip kernels (x-sorted z-strips + z-sweep) regardless of N       */
 
 typedef struct scribe_handle scribe_handle;
