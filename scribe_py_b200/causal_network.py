@@ -252,10 +252,11 @@ class causal_model(object):
         delays, node_ids, src, tgt, per = plan["delays"], plan["node_ids"], plan["src"], plan["tgt"], plan["per"]
         G = len(node_ids)
         self.rdi_results = {}
+        off = ~np.eye(G, dtype=bool)                      # jobs are target-major, sources ascending: the off-diagonal of M.T in C order
         for i, d in enumerate(delays):
-            M = np.full((G, G), np.nan)
-            M[src, tgt] = vals[i * per:(i + 1) * per]
-            self.rdi_results[d] = self._frame(M, node_ids)
+            Mt = np.full((G, G), np.nan)
+            Mt[off] = vals[i * per:(i + 1) * per]
+            self.rdi_results[d] = self._frame(Mt.T, node_ids)
         self.rdi_results["MAX"] = self.__extract_max_rdi_value_delay()[0]
         return self.rdi_results
 
