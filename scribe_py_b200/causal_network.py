@@ -257,7 +257,7 @@ class causal_model(object):
             Mt = np.full((G, G), np.nan)
             Mt[off] = vals[i * per:(i + 1) * per]
             self.rdi_results[d] = self._frame(Mt.T, node_ids)
-        self.rdi_results["MAX"] = self.__extract_max_rdi_value_delay()[0]
+        self.rdi_results["MAX"] = self.__extract_max_rdi_value_delay(want_delays=False)[0]
         return self.rdi_results
 
     # ------------------------------------------------------------------ cRDI
@@ -325,21 +325,25 @@ class causal_model(object):
             return frame.to_numpy(dtype=dtype)
         return frame.loc[node_ids, node_ids].to_numpy(dtype=dtype)
 
-    def __extract_max_rdi_value_delay(self):
+    def __extract_max_rdi_value_delay(self, want_delays=True):
         """Max over delays and the delay attaining it; strict '>' so the first delay wins ties, the diagonal
-        keeps -inf / NaN (causal_network.py:295-311, without the removed np.int)."""
+        keeps -inf / NaN (causal_network.py:295-311, without the removed np.int).  want_delays=False skips the
+        (object-typed) delay matrix, which rdi() itself never uses."""
         node_ids = list(self.node_ids)
         G = len(node_ids)
         val = np.full((G, G), -np.inf)
-        arg = np.full((G, G), np.nan, dtype=object)
+        arg = np.full((G, G), np.nan, dtype=object) if want_delays else None
         for delay, frame in self.rdi_results.items():
             if isinstance(delay, str) and delay == "MAX":
                 continue
             M = self.__square(frame, node_ids)
             better = M > val
             np.fill_diagonal(better, False)
-            val[better] = M[better]
-            arg[better] = delay
+            np.copyto(val, M, where=better)
+            if want_delays:
+                arg[better] = delay
+        if not want_delays:
+            return self._frame(val, node_ids), None
         return self._frame(val, node_ids), pd.DataFrame(arg, index=node_ids, columns=node_ids, dtype=object)
 
     def __extract_top_incoming_nodes_delays(self, max_rdi_values, max_rdi_delays, k_nodes):
