@@ -214,11 +214,13 @@ def ours_arm(args):
 
     def step_resident():
         flush.fill_(1)
+        torch.cuda.current_stream().synchronize()        # the library runs on its own stream: the flush must be complete first
         vals = model._rdi_execute(plan)
         return vals, h.stats()
 
     def step_e2e():
         flush.fill_(1)
+        torch.cuda.current_stream().synchronize()
         m = S.causal_model(frame)
         res = m.rdi(DELAYS)
         return res, h.stats()

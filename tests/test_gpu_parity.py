@@ -512,3 +512,17 @@ def test_rdi_fast_path_equals_generic_job_loop(S, est):
         ref = o.cumi(x, y, z, bw=0.2) if est == "cumi" else o.cmi(x, y, z)
         j01 = int(np.nonzero((jobs["src"] == 0) & (jobs["dst"] == 1) & (jobs["delay"] == 1))[0][0])
         assert close(fast[j01], ref, TOL_KDE if est == "cumi" else TOL_EXACT)
+
+
+@pytest.mark.gpu
+def test_mi_sweep_ragged_sizes(S):
+    """mi on the windowed sweep for sizes around the chunk boundaries and n <= k (eps = inf): == dense kernel == oracle"""
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 5, 6, 7, 31, 32, 33, 64, 65, 255, 257, 513):
+        x = np.round(rng.standard_normal((n, 1)), 1); y = x + rng.standard_normal((n, 1))
+        a = S.information_estimators.ksg_debug("mi", x, y, path="dense")
+        b = S.information_estimators.ksg_debug("mi", x, y, path="sweep")
+        assert np.array_equal(a["eps"], b["eps"]), n
+        assert np.array_equal(np.asarray(a["counts"])[:3], np.asarray(b["counts"])[:3]), n
+        eps, cnt = o.knn_counts(np.concatenate((x, y), axis=1), [(0, 1), (0,), (1,)], 5)
+        assert np.array_equal(b["eps"], eps) and np.array_equal(np.asarray(b["counts"])[:3], cnt), n
