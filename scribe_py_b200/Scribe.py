@@ -30,6 +30,53 @@ def _layer_frame(adata, genes, key):
     return df
 
 
+def _normalised_layers_pandas(adata, genes, t0_key, t1_key, normalize):
+    """Scribe.py:88-121 with the reference's own pandas expressions.  Returns S, Y gene-major (genes x cells) and the gene order."""
+    spliced = _layer_frame(adata, genes, t0_key)
+    velocity = _layer_frame(adata, genes, t1_key)
+    velocity[pd.isna(velocity)] = 0
+    if normalize:                                    # Scribe.py:104-106, same pandas expressions
+        spliced = (spliced - spliced.mean()) / (spliced.max() - spliced.min())
+        velocity = (velocity - velocity.mean()) / (velocity.max() - velocity.min())
+    y = (spliced + velocity) if t1_key == 'velocity' else velocity            # Scribe.py:121
+    S = np.ascontiguousarray(spliced.to_numpy(dtype=np.float64).T)
+    Y = np.ascontiguousarray(y.to_numpy(dtype=np.float64).T)
+    return S, Y, list(spliced.columns)
+
+
+def _normalised_layers(adata, genes, t0_key, t1_key, normalize):
+    """The same result computed gene-major in numpy -- one transposed copy per layer instead of five frame-sized pandas
+    temporaries -- when that is provably the same arithmetic: dense float64 layers without NaN in the t0 layer, and a
+    check on a few genes that the pandas expressions give bit-identical numbers with the installed pandas (its column
+    mean is a pairwise sum over a contiguous column; a different pandas build may sum differently, in which case
+    everything goes through pandas).  Anything else takes the pandas path."""
+    sub = adata[:, genes]
+    a, b = sub.layers[t0_key], sub.layers[t1_key]
+    ok = normalize and all(isinstance(m, np.ndarray) and m.dtype == np.float64 and m.ndim == 2 for m in (a, b)) and a.shape == b.shape \
+        and a.shape[0] > 0
+    if not ok:
+        return _normalised_layers_pandas(adata, genes, t0_key, t1_key, normalize)
+    At = np.ascontiguousarray(a.T)
+    if np.isnan(At).any():
+        return _normalised_layers_pandas(adata, genes, t0_key, t1_key, normalize)
+    Bt = np.array(b.T, dtype=np.float64, order="C")
+    Bt[np.isnan(Bt)] = 0
+
+    def norm(M):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = M.sum(axis=1) / M.shape[1]
+            return (M - mean[:, None]) / (M.max(axis=1) - M.min(axis=1))[:, None]
+
+    S, V = norm(At), norm(Bt)
+    Y = (S + V) if t1_key == 'velocity' else V
+    order = list(sub.var_names)
+    probe = sorted(set([0, len(order) // 2, len(order) - 1]))
+    Sp, Yp, _ = _normalised_layers_pandas(adata, [order[i] for i in probe], t0_key, t1_key, normalize)
+    if not (np.array_equal(Sp, S[probe], equal_nan=True) and np.array_equal(Yp, Y[probe], equal_nan=True)):
+        return _normalised_layers_pandas(adata, genes, t0_key, t1_key, normalize)
+    return S, Y, order
+
+
 def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None, t0_key='spliced', t1_key='velocity',
                                  normalize=True, drop_zero_cells=True, copy=False):
     """Infer a causal network from dynamics-coupled single-cell measurements: for every TF g_a and target g_b,
@@ -53,17 +100,8 @@ def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None,
         guides = np.setdiff1d(guides, ['*', 'nan', 'neg'])
 
     genes = np.unique(TFs + Targets)
-    spliced = _layer_frame(adata, genes, t0_key)
-    velocity = _layer_frame(adata, genes, t1_key)
-    velocity[pd.isna(velocity)] = 0
-    if normalize:                                    # Scribe.py:104-106, same pandas expressions
-        spliced = (spliced - spliced.mean()) / (spliced.max() - spliced.min())
-        velocity = (velocity - velocity.mean()) / (velocity.max() - velocity.min())
-    y = (spliced + velocity) if t1_key == 'velocity' else velocity            # Scribe.py:121
-
-    col = {g: i for i, g in enumerate(spliced.columns)}
-    S = np.ascontiguousarray(spliced.to_numpy(dtype=np.float64).T)
-    Y = np.ascontiguousarray(y.to_numpy(dtype=np.float64).T)
+    S, Y, gene_order = _normalised_layers(adata, genes, t0_key, t1_key, normalize)
+    col = {g: i for i, g in enumerate(gene_order)}
     ia = np.array([col[g] for g in TFs], dtype=np.int32)
     ib = np.array([col[g] for g in Targets], dtype=np.int32)
     # job order: target-major so a rank's slab shares y/z columns

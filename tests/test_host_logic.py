@@ -191,3 +191,33 @@ def test_pair_delay_job_table_slices():
     assert t[5:9] is t[5:9]                                  # a repeated slab request is served from the one-entry cache
     with pytest.raises(TypeError):
         t[3]
+
+
+def test_coupling_normalisation_fast_path_is_bit_identical():
+    """the gene-major numpy normalisation of causal_net_dynamics_coupling must equal the reference's pandas expressions
+    bit for bit (it verifies itself on a few genes and otherwise falls back); odd inputs take the pandas path"""
+    import scipy.sparse as sp
+    from scribe_py_b200 import Scribe as sc
+    rng = np.random.default_rng(11)
+    N, G = 700, 23
+    spl = rng.gamma(2., 1., (N, G)); spl[rng.random((N, G)) < 0.25] = 0; spl[:, 5] = 2.0          # one constant gene: 0/0
+    vel = 0.1 * rng.standard_normal((N, G)); vel[rng.random((N, G)) < 0.01] = np.nan
+    genes = ["g%02d" % i for i in range(G)]
+    want = np.unique(genes[3:20])
+    cases = {
+        "c-order": (spl, vel), "f-order": (np.asfortranarray(spl), np.asfortranarray(vel)),
+        "float32": (spl.astype(np.float32), vel.astype(np.float32)),
+        "sparse": (sp.csr_matrix(spl), sp.csr_matrix(np.nan_to_num(vel))),
+    }
+    for name, (a, b) in cases.items():
+        for t1 in ("velocity", "other"):
+            ad = recipes.FakeAnnData({"spliced": a, t1: b}, genes)
+            with np.errstate(all="ignore"):
+                ref = sc._normalised_layers_pandas(ad, want, "spliced", t1, True)
+                got = sc._normalised_layers(ad, want, "spliced", t1, True)
+            assert got[2] == ref[2], name
+            assert np.array_equal(got[0], ref[0], equal_nan=True) and np.array_equal(got[1], ref[1], equal_nan=True), (name, t1)
+            assert got[0].flags["C_CONTIGUOUS"] and got[0].shape == (len(want), N)
+    ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
+    raw = sc._normalised_layers(ad, want, "spliced", "velocity", False)                     # normalize=False: pandas path
+    assert np.array_equal(raw[0], spl[:, 3:20].T)
