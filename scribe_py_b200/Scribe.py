@@ -106,7 +106,7 @@ def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None,
     ib = np.array([col[g] for g in Targets], dtype=np.int32)
     # job order: target-major so a rank's slab shares y/z columns
     bb, aa = np.meshgrid(np.arange(len(Targets)), np.arange(len(TFs)), indexing="ij")
-    names_differ = np.array([[TFs[a] != Targets[b] for a in range(len(TFs))] for b in range(len(Targets))])
+    names_differ = np.asarray(Targets, dtype=object)[:, None] != np.asarray(TFs, dtype=object)[None, :]     # skip g_a == g_b (Scribe.py:112)
     aa, bb = aa[names_differ], bb[names_differ]
     src, dst = ia[aa], ib[bb]
 
