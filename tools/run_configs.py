@@ -126,7 +126,10 @@ def run_c3(G, N, n_check):
     ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
     h = _lib.default_handle()
     S.causal_net_dynamics_coupling(recipes.FakeAnnData({"spliced": spl[:, :8], "velocity": vel[:, :8]}, genes[:8]))   # warm-up
-    barrier(); t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); barrier(); wall = time.perf_counter() - t
+    walls = []
+    for _ in range(3):              # the first full-size call also pays for the growth of the device workspaces
+        barrier(); t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); barrier(); walls.append(time.perf_counter() - t)
+    wall = min(walls)
     st = h.stats()
     M = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
     s = (spl - spl.mean(0)) / (spl.max(0) - spl.min(0)); v = (vel - vel.mean(0)) / (vel.max(0) - vel.min(0))
@@ -139,7 +142,8 @@ def run_c3(G, N, n_check):
     ref = cpu_check(_cmi_job, args)
     return report("C3 dynamics coupling %d genes x %d cells" % (G, N), G * (G - 1), wall, st,
                   {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()) if WORLD == 1 else None, "parity_jobs": n_check,
-                   "estimator_ms_last_chunk": st["estimator_ms"], "mean_cells_kept": float(np.mean([len(a[0]) for a in args]))})
+                   "estimator_ms_last_chunk": st["estimator_ms"], "mean_cells_kept": float(np.mean([len(a[0]) for a in args])),
+                   "wall_s_each_call": walls})
 
 
 def init_distributed():
