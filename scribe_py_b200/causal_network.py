@@ -348,22 +348,30 @@ class causal_model(object):
 
     def __extract_top_incoming_nodes_delays(self, max_rdi_values, max_rdi_delays, k_nodes):
         """Per target the k_nodes+1 strongest sources by streaming replace-first-minimum
-        (causal_network.py:316-333)."""
+        (causal_network.py:316-333).  The reference's double loop (targets x sources) is run here as one pass over
+        the sources that updates all targets at once: identical slot contents and slot order, G numpy steps
+        instead of G^2 Python iterations."""
         node_ids = list(self.node_ids)
+        G, K = len(node_ids), k_nodes + 1
         V = self.__square(max_rdi_values, node_ids)
         Dl = self.__square(max_rdi_delays, node_ids, dtype=object)
+        vals = np.full((G, K), -np.inf)                    # [target, slot]
+        who = np.full((G, K), -1, dtype=np.int64)
+        tgt = np.arange(G)
+        for a_i in range(G):
+            lo = vals.min(axis=1)
+            slot = vals.argmin(axis=1)                     # FIRST minimal slot, like list.index(min(...))
+            upd = V[a_i, :] > lo                           # strict: an equal value never replaces; NaN never enters
+            upd[a_i] = False                               # a source is not its own regulator
+            t = tgt[upd]
+            vals[t, slot[upd]] = V[a_i, upd]
+            who[t, slot[upd]] = a_i
         top_nodes, top_delays, top_values = {}, {}, {}
         for b_i, b in enumerate(node_ids):
-            nodes = [None] * (k_nodes + 1); dls = [np.nan] * (k_nodes + 1); vals = [-np.inf] * (k_nodes + 1)
-            col = V[:, b_i]
-            for a_i, a in enumerate(node_ids):
-                if a_i == b_i:
-                    continue
-                lo = min(vals)
-                if col[a_i] > lo:
-                    s = vals.index(lo)
-                    nodes[s] = a; dls[s] = Dl[a_i, b_i]; vals[s] = col[a_i]
-            top_nodes[b], top_delays[b], top_values[b] = nodes, dls, vals
+            w = who[b_i]
+            top_nodes[b] = [node_ids[i] if i >= 0 else None for i in w]
+            top_delays[b] = [Dl[i, b_i] if i >= 0 else np.nan for i in w]
+            top_values[b] = [float(v) for v in vals[b_i]]
         return top_nodes, top_delays, top_values
 
     # ------------------------------------------------------------------ evaluation (pass-through)

@@ -221,3 +221,39 @@ def test_coupling_normalisation_fast_path_is_bit_identical():
     ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
     raw = sc._normalised_layers(ad, want, "spliced", "velocity", False)                     # normalize=False: pandas path
     assert np.array_equal(raw[0], spl[:, 3:20].T)
+
+
+def test_top_incoming_matches_reference_loop(S):
+    """the all-targets-at-once form of the streaming top-(L+1) selection == the reference's double loop
+    (causal_network.py:316-333), slot for slot, on matrices with ties, -inf and NaN diagonals"""
+    def loop_version(V, Dl, node_ids, k_nodes):
+        top_nodes, top_delays, top_values = {}, {}, {}
+        for b_i, b in enumerate(node_ids):
+            nodes = [None] * (k_nodes + 1); dls = [np.nan] * (k_nodes + 1); vals = [-np.inf] * (k_nodes + 1)
+            for a_i, a in enumerate(node_ids):
+                if a_i == b_i:
+                    continue
+                lo = min(vals)
+                if V[a_i, b_i] > lo:
+                    s = vals.index(lo)
+                    nodes[s] = a; dls[s] = Dl[a_i, b_i]; vals[s] = V[a_i, b_i]
+            top_nodes[b], top_delays[b], top_values[b] = nodes, dls, vals
+        return top_nodes, top_delays, top_values
+
+    rng = np.random.default_rng(21)
+    for G, L, ties in ((9, 1, False), (17, 2, True), (6, 4, True), (3, 3, False)):
+        genes = ["g%02d" % i for i in range(G)]
+        V = rng.standard_normal((G, G))
+        if ties:
+            V = np.round(V, 0)                                   # many equal values, also equal to the running minimum
+        np.fill_diagonal(V, -np.inf)
+        Dl = rng.integers(1, 4, (G, G)).astype(object)
+        m = S.causal_model(pd.DataFrame(rng.standard_normal((G, 30)), index=pd.Index(genes, name="GENE_ID")))
+        fn = getattr(m, "_causal_model__extract_top_incoming_nodes_delays")
+        got = fn(pd.DataFrame(V, index=genes, columns=genes), pd.DataFrame(Dl, index=genes, columns=genes, dtype=object), L)
+        ref = loop_version(V, Dl, genes, L)
+        for gd, rd in zip(got, ref):
+            for b in genes:
+                assert len(gd[b]) == L + 1
+                for x, y in zip(gd[b], rd[b]):
+                    assert (x == y) or (isinstance(x, float) and isinstance(y, float) and np.isnan(x) and np.isnan(y)), (G, L, b, gd[b], rd[b])
