@@ -251,6 +251,24 @@ void sort_segments(scribe_handle* h, const double* keys_in, int n_seg, int64_t s
     h->st.kernel_launches += 2;
 }
 
+// argsort of the key columns `keyspec` (indices into h->cols, stride doubles apart) -> h->perm [keyspec.size()][stride]
+void argsort_key_columns(scribe_handle* h, const std::vector<int>& keyspec, const std::vector<int>& keylen, int64_t stride)
+{
+    const int64_t nk = (int64_t)keyspec.size();
+    h->keys_in.ensure(sizeof(double) * nk * stride);
+    h->perm.ensure(sizeof(int32_t) * nk * stride);
+    h->keyspecs.ensure(sizeof(int) * nk);
+    CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
+    for (int64_t k0 = 0; k0 < nk; k0 += 65535) {          // key columns -> one contiguous block (gridDim.y limit)
+        dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min<int64_t>(65535, nk - k0));
+        select_columns_kernel<<<grid, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
+                                                           h->keys_in.as<double>() + (size_t)k0 * stride);
+        CU(cudaGetLastError());
+        h->st.kernel_launches++;
+    }
+    sort_segments(h, h->keys_in.as<double>(), (int)nk, stride, keylen, h->perm.as<int32_t>());
+}
+
 using KdeFn = void (*)(const JobDesc*, int, const int*, double, double*);
 KdeFn pick_kde(int dp) {
     switch (dp) {
@@ -674,18 +692,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             if (ordered) {                                    // argsort of every gene's z column (its own past), per delay
                 std::vector<int> keyspec((size_t)nk), keylen((size_t)nk);
                 for (int64_t kq = 0; kq < nk; kq++) { keyspec[kq] = (int)(kq * 3 + 2); keylen[kq] = lay.n_of[kq / G]; }
-                h->keys_in.ensure(sizeof(double) * nk * stride);
-                h->perm.ensure(sizeof(int32_t) * nk * stride);
-                h->keyspecs.ensure(sizeof(int) * nk);
-                CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
-                for (int64_t k0 = 0; k0 < nk; k0 += 65535) {
-                    dim3 g2((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min<int64_t>(65535, nk - k0));
-                    select_columns_kernel<<<g2, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
-                                                                     h->keys_in.as<double>() + (size_t)k0 * stride);
-                    CU(cudaGetLastError());
-                    h->st.kernel_launches++;
-                }
-                sort_segments(h, h->keys_in.as<double>(), (int)nk, stride, keylen, h->perm.as<int32_t>());
+                argsort_key_columns(h, keyspec, keylen, stride);
             }
             tr.lap("fast: key select + argsort");
             for (int t = 0; t < lay.n_delays; t++) h->st.point_pairs += per_delay[t] * (int64_t)lay.n_of[t] * lay.n_of[t];
@@ -828,19 +835,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
                 const int sp = colidx[j * D + D - 1];
                 if (slot[sp] < 0) { slot[sp] = (int)keyspec.size(); keyspec.push_back(sp); keylen.push_back(hj[j].n); }
             }
-            const int nk = (int)keyspec.size();
-            h->keys_in.ensure(sizeof(double) * nk * stride);
-            h->perm.ensure(sizeof(int32_t) * nk * stride);
-            h->keyspecs.ensure(sizeof(int) * nk);
-            CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
-            for (int k0 = 0; k0 < nk; k0 += 65535) {      // key columns -> one contiguous block (gridDim.y limit)
-                dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min(65535, nk - k0));
-                select_columns_kernel<<<grid, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
-                                                                   h->keys_in.as<double>() + (size_t)k0 * stride);
-                CU(cudaGetLastError());
-                h->st.kernel_launches++;
-            }
-            sort_segments(h, h->keys_in.as<double>(), nk, stride, keylen, h->perm.as<int32_t>());
+            argsort_key_columns(h, keyspec, keylen, stride);
             for (int64_t j = 0; j < nj; j++) hj[j].perm = h->perm.as<int32_t>() + (size_t)slot[colidx[j * D + D - 1]] * stride;
             ordered = true;
         }
