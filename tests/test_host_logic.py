@@ -111,7 +111,17 @@ def _gloo_worker(rank, world, port, q):
     s._lib.default_handle = lambda device=None: fake
     X, genes, delays = recipes.gv_d()
     r = s.causal_model(pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID"))).rdi(delays)
-    q.put((rank, ok, seen, fake.calls, r[1].to_numpy(dtype=float), r[2].to_numpy(dtype=float)))
+    # cRDI = two sharded phases with the all-gather in between (conditioning sets come from the gathered RDI matrix),
+    # and the dynamics-coupling driver: both must give every rank the complete result
+    runs, genes_e, delays_e = recipes.gv_e()
+    m = s.causal_model(recipes.multi_run_frame(runs, genes_e))
+    m.rdi(delays_e)
+    crdi = m.crdi(L=2).to_numpy(dtype=float)
+    spl, vel, genes_c = recipes.gv_c()
+    ad = recipes.FakeAnnData({"spliced": spl.copy(), "velocity": vel.copy()}, genes_c)
+    s.causal_net_dynamics_coupling(ad, TFs=genes_c[:3], Targets=genes_c[:4])
+    coup = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
+    q.put((rank, ok, seen, fake.calls[:1], r[1].to_numpy(dtype=float), r[2].to_numpy(dtype=float), crdi, coup))
     dist.destroy_process_group()
 
 
@@ -128,11 +138,13 @@ def test_two_rank_gloo_sharding(golden):
     for p in procs:
         p.join(timeout=60)
     assert res[0][2] == [(0, 51)] and res[1][2] == [(51, 101)]
-    for rank, ok, seen, calls, r1, r2 in res:
+    for rank, ok, seen, calls, r1, r2, crdi, coup in res:
         assert ok
         assert calls == [12]                              # 24 jobs (12 ordered pairs x 2 delays) split evenly
         assert np.allclose(r1, golden["d_rdi_1"], atol=1e-12, rtol=0, equal_nan=True)
         assert np.allclose(r2, golden["d_rdi_2"], atol=1e-12, rtol=0, equal_nan=True)
+        assert np.allclose(crdi, golden["e_crdi_L2"], atol=1e-12, rtol=0, equal_nan=True)
+        assert np.allclose(coup, golden["c_matrix"][:3, :4], atol=1e-12, rtol=0)
 
 
 def test_load_anndata_branches_as_runs(S):
