@@ -29,6 +29,9 @@ namespace scribe {
 #ifndef SWEEPW_UNROLL
 #define SWEEPW_UNROLL 8
 #endif
+#ifndef SWEEPW_MERGED
+#define SWEEPW_MERGED 1                   // one marked-candidate loop for all query slots of a lane (0: one loop per slot)
+#endif
 #ifndef SWEEPW_MIN_CTAS
 #define SWEEPW_MIN_CTAS 10                // 102 registers: 20 resident warps per SM; measured equal at N = 2000 and 8 % faster at N = 20 000 than 12 CTAs / 80 registers
 #endif
@@ -253,6 +256,29 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             #pragma unroll
             for (int q = Q0; q < Q; q++) mask[q] |= mb[q] << jb;
             if (!fine && jb + UNR < 32) continue;
+#if SWEEPW_MERGED
+            // One loop for all query slots of the lane: every trip takes the next marked candidate of EACH slot, so the exact
+            // re-tests of the slots are independent instruction streams (the loop is latency-bound: LDS -> DADD -> DSETP
+            // chains at ~25 % lane efficiency) and the trip count is max over lanes of max over slots, not the sum of the
+            // per-slot maxima.
+            unsigned any = 0u;
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) { if (q == selfq) mask[q] &= ~(1u << lane); any |= mask[q]; }
+            while (any) {
+                any = 0u;
+                #pragma unroll
+                for (int q = Q0; q < Q; q++) {
+                    const bool has = mask[q] != 0u;
+                    const int j = has ? __ffs(mask[q]) - 1 : 0;
+                    mask[q] &= mask[q] - 1;                                    // 0 stays 0
+                    any |= mask[q];
+                    double dd = abs_f64(qc[q][KEY] - bk[j]);
+                    #pragma unroll
+                    for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
+                    if (has && dd < L[q][KL - 1]) topk_insert<KL>(L[q], dd);   // exact test; NaN (padding) never passes
+                }
+            }
+#else
             #pragma unroll
             for (int q = Q0; q < Q; q++) {
                 if (q == selfq) mask[q] &= ~(1u << lane);
@@ -264,7 +290,11 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                     for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
                     if (dd < L[q][KL - 1]) topk_insert<KL>(L[q], dd);          // exact test; NaN (padding) never passes
                 }
-                if (fine) T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack));
+            }
+#endif
+            if (fine) {
+                #pragma unroll
+                for (int q = Q0; q < Q; q++) T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack));
             }
         }
     };

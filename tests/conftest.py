@@ -17,3 +17,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_configs():
+    """outputs of the unmodified reference on the named BASELINE configs (tests/golden/make_golden_configs.py)"""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_configs.npz")))

@@ -104,6 +104,39 @@ def rdi_synthetic(G, T, seed):
     return E[:, 50:]
 
 
+def ar_panel(G, T, seed):
+    """cheap autocorrelated expression panel with sparse lagged couplings (vectorised over genes): the C4 / C5 generator
+    (BASELINE configs[3], configs[4]; C5 z-scores each gene afterwards, as causal_model.normalize() would)"""
+    rng = np.random.default_rng(seed)
+    E = np.zeros((G, T + 60)); E[:, :12] = rng.standard_normal((G, 12))
+    par = rng.integers(0, G, (G, 2)); dl = rng.choice([1, 5, 10], (G, 2)); co = rng.uniform(0.4, 0.9, (G, 2)) * rng.choice([-1, 1], (G, 2))
+    noise = 0.3 * rng.standard_normal((G, T + 60))
+    for t in range(12, T + 60):
+        E[:, t] = 0.9 * E[:, t - 1] + noise[:, t] + co[:, 0] * np.tanh(E[par[:, 0], t - dl[:, 0]]) + co[:, 1] * np.tanh(E[par[:, 1], t - dl[:, 1]])
+    return E[:, 60:]
+
+
+def zscore_rows(E):
+    return (E - E.mean(1, keepdims=True)) / E.std(1, keepdims=True)
+
+
+def coupling_panel(G, N, seed=3):
+    """C3 generator (BASELINE configs[2]): spliced = gamma(2,1) with 20 % zeros, velocity = sparse linear coupling of two
+    parents - 0.2 * spliced + noise.  Returns cells x genes layers and the gene names."""
+    rng = np.random.default_rng(seed)
+    spl = rng.gamma(2., 1., (N, G)); spl[rng.random((N, G)) < 0.2] = 0
+    par = rng.integers(0, G, (G, 2)); co = rng.uniform(-0.5, 0.5, (G, 2))
+    vel = co[:, 0] * (spl[:, par[:, 0]] - spl[:, par[:, 0]].mean(0)) + co[:, 1] * (spl[:, par[:, 1]] - spl[:, par[:, 1]].mean(0)) \
+        - 0.2 * spl + 0.1 * rng.standard_normal((N, G))
+    return spl, vel, ["g%04d" % i for i in range(G)]
+
+
+# gene subsets of the named configs on which the UNMODIFIED reference was run (tests/golden/make_golden_configs.py)
+C3_TFS, C3_TARGETS = [3, 77, 140, 251, 402], [9, 77, 118, 205, 251, 333, 420, 499]
+C4_GENES = [5, 23, 61, 99, 134, 170, 198]
+C5_GENES = [12, 345, 678, 901]
+
+
 class FakeAnnData:
     """Duck-typed AnnData: var_names / obs_names (pandas Index), layers (cells x genes), uns, [:, genes]."""
 
