@@ -105,6 +105,8 @@ void scribe_destroy(scribe_handle* h);
 int  scribe_device_info(scribe_handle* h, int32_t* sm_count, int32_t* clock_khz, int64_t* mem_bytes,
                         char* name, int32_t name_len);
 int  scribe_get_stats(scribe_handle* h, scribe_stats* out);
+/* CUDA device ordinal the handle computes on (the process group's collectives must use the same device). */
+int  scribe_device_index(scribe_handle* h);
 
 /* ---- estimator level: replaces a single call of information_estimators.mi/cmi/umi/cumi -------- */
 /* x: dx*n, y: dy*n, z: dz*n doubles (z == NULL and dz == 0 for mi/umi), already normalised by the caller
@@ -146,12 +148,39 @@ int scribe_mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
 /* S, Y: n_genes rows of n_cells doubles.  S = normalised t0 layer (x and z columns, Scribe.py:119,:123);
  * Y = the y column per gene (S + V when t1_key == 'velocity', else V; Scribe.py:121). */
 int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, int64_t n_genes, int64_t n_cells);
+/* The same from the RAW layers, normalised on the device: t0_layer / t1_layer are the AnnData layers as they are stored,
+ * n_cells rows of n_genes doubles (dense, cell-major).  NaN of the t1 layer -> 0 (Scribe.py:101); normalize != 0 applies
+ * (layer - mean) / (max - min) per gene (Scribe.py:104-106) with numpy's summation order for the mean; Y = S + V when
+ * y_is_sum (t1_key == 'velocity', Scribe.py:121) else V.  *t0_has_nan != 0 on return means the t0 layer holds NaN, which
+ * pandas would skip in the mean: the caller must then normalise on the host and use scribe_upload_coupling. */
+int scribe_upload_coupling_raw(scribe_handle* h, const double* t0_layer, const double* t1_layer, int64_t n_cells, int64_t n_genes,
+                               int32_t normalize, int32_t y_is_sum, int32_t* t0_has_nan);
+/* One row of the resident S (which == 0) or Y (which == 1) matrix back to the host (n_cells doubles): lets the caller check
+ * the device normalisation against the reference's pandas expression on a few genes. */
+int scribe_read_coupling_row(scribe_handle* h, int32_t which, int64_t gene, double* out_row);
 /* job j: I(S[src[j]] ; Y[dst[j]] | S[dst[j]]); drop_zero_cells keeps cells with (x + y) + z > 0
  * (Scribe.py:125-128).  n_eff (may be NULL) receives the cells kept per job. */
 int scribe_coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs,
                          int32_t drop_zero_cells, const scribe_opts* opts, double* out_host, int32_t* n_eff);
 int scribe_coupling_jobs_dev(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n_jobs,
                              int32_t drop_zero_cells, const scribe_opts* opts, double* out_dev, int32_t* n_eff);
+
+/* ---- consumers of the causal matrix --------------------------------------------------- */
+/* Context likelihood of relatedness (Scribe.CLR, Scribe/Scribe.py:142-176) of a rows x cols score matrix (row-major, host):
+ * z-scores of round(M, 10) against the row (both_dims: and column) mean / std (ddof = 1) of M, negatives clipped to 0,
+ * sqrt((z_row^2 + z_col^2) / 2).  A square matrix is z-scored against the statistics of ROW j, as the reference's broadcast
+ * does (Scribe.py:151-154). */
+int scribe_clr(scribe_handle* h, const double* M, int64_t rows, int64_t cols, int32_t both_dims, double* out);
+/* The n_top strongest edges of a square n x n score matrix, strongest first (vis_causal_net, Scribe/plot/networks.py:34-47):
+ * an entry smaller than its transpose (the weaker direction of a reciprocal pair) and NaN entries are dropped; ties keep
+ * row-major order.  src/dst/weight receive *n_found <= n_top edges. */
+int scribe_top_edges(scribe_handle* h, const double* M, int64_t n, int64_t n_top, int32_t* src, int32_t* dst, double* weight,
+                     int64_t* n_found);
+/* ROC curve and AUROC of an n x n score matrix against a truth mask (causal_model.roc, Scribe/causal_network.py:337-389):
+ * off-diagonal edges, source-major, ranked by descending score (stable); truth[i*n+j] != 0 marks a true edge.  fpr/tpr
+ * (may be NULL) receive n*(n-1)+1 points when no score is NaN.  SCRIBE_E_DOMAIN when there is no true or no false edge
+ * (the reference divides by zero there). */
+int scribe_roc(scribe_handle* h, const double* scores, const uint8_t* truth, int64_t n, double* auroc, double* fpr, double* tpr);
 
 #ifdef __cplusplus
 }

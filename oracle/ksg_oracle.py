@@ -304,8 +304,8 @@ def crdi_jobs(max_val, max_delay, L):
     return jobs
 
 
-def crdi_columns(expr_runs, a, b, delay, cond, cond_delays):
-    """x, y, z of one cRDI job following the multi-run branch (cn:257-283)."""
+def crdi_columns(expr_runs, a, b, delay, cond, cond_delays, differential=False):
+    """x, y, z of one cRDI job following the multi-run branch (cn:257-283); differential: y_t = e_b[tau-1+t] - e_b[tau+t] (cn:271)."""
     L = len(cond)
     tau = max(list(cond_delays) + [delay])
     xs, ys, zs = [], [], []
@@ -313,7 +313,7 @@ def crdi_columns(expr_runs, a, b, delay, cond, cond_delays):
         eb = expr_runs[b][r]; ea = expr_runs[a][r]
         n = len(eb) - tau
         xs.append(ea[tau - delay:tau - delay + n])
-        ys.append(eb[tau:tau + n])
+        ys.append(eb[tau - 1:tau - 1 + n] - eb[tau:tau + n] if differential else eb[tau:tau + n])
         zc = [eb[tau - 1:tau - 1 + n]]
         for i in range(L):                                  # each new column is PREPENDED (cn:277)
             e3 = expr_runs[cond[i]][r]
@@ -322,15 +322,16 @@ def crdi_columns(expr_runs, a, b, delay, cond, cond_delays):
     return np.concatenate(xs), np.concatenate(ys), np.concatenate(zs, axis=0)
 
 
-def crdi(expr_runs, rdi_res, delays, L=1, uniformization=False, k=5):
+def crdi(expr_runs, rdi_res, delays, L=1, uniformization=False, k=5, differential_mode=False):
+    """differential_mode: y differenced and normalization=True, i.e. every role divided by np.std of its whole array (cn:219-221)."""
     G = len(expr_runs)
     val, arg = max_over_delays(rdi_res, delays)
     jobs = crdi_jobs(val, arg, L)
     est = cumi if uniformization else cmi
     M = np.full((G, G), np.nan)
     for (a, b), (d, cn, cd) in jobs.items():
-        x, y, z = crdi_columns(expr_runs, a, b, d, cn, cd)
-        M[a, b] = est(x, y, z, k=k)
+        x, y, z = crdi_columns(expr_runs, a, b, d, cn, cd, differential_mode)
+        M[a, b] = est(x, y, z, k=k, normalization=True) if differential_mode else est(x, y, z, k=k)
     return M
 
 

@@ -14,7 +14,7 @@ from scipy.sparse import issparse
 from . import _lib
 from . import distributed as _dist
 
-CLR_DDOF = 1
+CLR_DDOF = 1      # the reference's module constant (Scribe.py:8); scribe_clr uses ddof = 1
 
 __all__ = ["causal_net_dynamics_coupling", "CLR", "check_symmetric"]
 
@@ -77,11 +77,50 @@ def _normalised_layers(adata, genes, t0_key, t1_key, normalize):
     return S, Y, order
 
 
-def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None, t0_key='spliced', t1_key='velocity',
-                                 normalize=True, drop_zero_cells=True, copy=False):
-    """Infer a causal network from dynamics-coupled single-cell measurements: for every TF g_a and target g_b,
-    I(spliced[g_a]; y[g_b] | spliced[g_b]) with y = spliced + velocity when t1_key == 'velocity', else the
-    t1 layer itself.  Arguments and result are those of the reference (Scribe.py:10-64)."""
+def _dense_layers(adata, genes, t0_key, t1_key):
+    """The two layers restricted to `genes` (in that order) as dense cells x genes float64 arrays, without a copy when the
+    gene list is the AnnData's own column order (the reference goes through adata[:, genes] and a DataFrame, Scribe.py:88-99)."""
+    idx = adata.var_names.get_indexer(list(genes))
+    whole = len(idx) == len(adata.var_names) and np.array_equal(idx, np.arange(len(idx)))
+    out = []
+    for key in (t0_key, t1_key):
+        mat = adata.layers[key]
+        if issparse(mat):
+            mat = np.asarray(mat.todense())
+        mat = np.asarray(mat)
+        if not whole:
+            mat = mat[:, idx]
+        out.append(np.ascontiguousarray(mat, dtype=np.float64))
+    return out[0], out[1]
+
+
+def _upload_layers(h, adata, genes, t0_key, t1_key, normalize):
+    """Make S / Y of `genes` resident on the handle's device.  Preferred: the raw layers go up as they are and the device
+    normalises them (scribe_upload_coupling_raw; numpy's summation order, so the same float64 as the pandas expressions of
+    Scribe.py:104-106) -- checked on three probe genes against those pandas expressions; anything that does not fit (NaN in the
+    t0 layer, a pandas build that sums differently) is normalised on the host and uploaded with scribe_upload_coupling."""
+    order = list(genes)
+    y_is_sum = t1_key == 'velocity'
+    try:
+        a, b = _dense_layers(adata, order, t0_key, t1_key)
+        ok = a.ndim == 2 and a.shape == b.shape and a.shape[0] > 0 and hasattr(h, "upload_coupling_raw")
+    except Exception:
+        ok = False
+    if ok and h.upload_coupling_raw(a, b, normalize, y_is_sum):
+        probe = sorted(set([0, len(order) // 2, len(order) - 1]))
+        Sp, Yp, _ = _normalised_layers_pandas(adata, [order[i] for i in probe], t0_key, t1_key, normalize)
+        same = all(np.array_equal(h.read_coupling_row(0, g, a.shape[0]), Sp[i], equal_nan=True) and
+                   np.array_equal(h.read_coupling_row(1, g, a.shape[0]), Yp[i], equal_nan=True) for i, g in enumerate(probe))
+        if same:
+            return order
+    S, Y, order = _normalised_layers(adata, genes, t0_key, t1_key, normalize)
+    h.upload_coupling(S, Y)
+    return order
+
+
+def _coupling_plan(adata, TFs=None, Targets=None, t0_key='spliced', t1_key='velocity', normalize=True):
+    """Argument handling of causal_net_dynamics_coupling (Scribe.py:66-86) and the job table: every (TF, target) pair with
+    different names, target-major so that a rank's slab shares its targets' y / z columns."""
     if TFs is None:
         TFs = adata.var_names.tolist()
     else:
@@ -94,39 +133,52 @@ def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None,
         Targets = adata.var_names.intersection(Targets).tolist()
         if len(Targets) == 0:
             raise Exception("The adata object has no gene names from .var_name that intersect with the Targets list you provided")
-
-    if guide_keys is not None:                       # computed and unused, as in the reference (Scribe.py:80-86)
-        guides = np.unique(adata.obs[guide_keys].tolist())
-        guides = np.setdiff1d(guides, ['*', 'nan', 'neg'])
-
     genes = np.unique(TFs + Targets)
-    S, Y, gene_order = _normalised_layers(adata, genes, t0_key, t1_key, normalize)
-    col = {g: i for i, g in enumerate(gene_order)}
+    col = {g: i for i, g in enumerate(genes)}
     ia = np.array([col[g] for g in TFs], dtype=np.int32)
     ib = np.array([col[g] for g in Targets], dtype=np.int32)
-    # job order: target-major so a rank's slab shares y/z columns
     bb, aa = np.meshgrid(np.arange(len(Targets)), np.arange(len(TFs)), indexing="ij")
     names_differ = np.asarray(Targets, dtype=object)[:, None] != np.asarray(TFs, dtype=object)[None, :]     # skip g_a == g_b (Scribe.py:112)
     aa, bb = aa[names_differ], bb[names_differ]
-    src, dst = ia[aa], ib[bb]
+    return {"TFs": TFs, "Targets": Targets, "genes": genes, "aa": aa, "bb": bb, "src": np.ascontiguousarray(ia[aa]),
+            "dst": np.ascontiguousarray(ib[bb]), "t0_key": t0_key, "t1_key": t1_key, "normalize": normalize}
 
+
+def _coupling_execute(plan, drop_zero_cells=True):
+    """Evaluate the plan's pairs against the S / Y matrices resident on this rank's GPU; every rank gets every result."""
     h = _lib.default_handle()
-    h.upload_coupling(S, Y)
+    src, dst = plan["src"], plan["dst"]
     opts = _lib.make_opts(_lib.EST_CMI, 5)
 
-    def evaluate(lo, hi):
-        return h.coupling_jobs(src[lo:hi], dst[lo:hi], opts, drop_zero_cells)
+    def evaluate(lo, hi, out_dev_ptr=None):
+        return h.coupling_jobs(src[lo:hi], dst[lo:hi], opts, drop_zero_cells, out_dev_ptr=out_dev_ptr)
 
-    vals = _dist.sharded_evaluate(len(src), evaluate)
-    M = np.full((len(TFs), len(Targets)), np.nan)
-    M[aa, bb] = vals
-    causal_net = pd.DataFrame(M, index=TFs, columns=Targets)
-    adata.uns['causal_net'] = {"RDI": causal_net.fillna(0)}
+    return _dist.sharded_evaluate(len(src), evaluate, h)
+
+
+def causal_net_dynamics_coupling(adata, TFs=None, Targets=None, guide_keys=None, t0_key='spliced', t1_key='velocity',
+                                 normalize=True, drop_zero_cells=True, copy=False):
+    """Infer a causal network from dynamics-coupled single-cell measurements: for every TF g_a and target g_b,
+    I(spliced[g_a]; y[g_b] | spliced[g_b]) with y = spliced + velocity when t1_key == 'velocity', else the
+    t1 layer itself.  Arguments and result are those of the reference (Scribe.py:10-64)."""
+    plan = _coupling_plan(adata, TFs, Targets, t0_key, t1_key, normalize)
+    if guide_keys is not None:                       # computed and unused, as in the reference (Scribe.py:80-86)
+        guides = np.unique(adata.obs[guide_keys].tolist())
+        guides = np.setdiff1d(guides, ['*', 'nan', 'neg'])
+    _upload_layers(_lib.default_handle(), adata, plan["genes"], t0_key, t1_key, normalize)
+    vals = _coupling_execute(plan, drop_zero_cells)
+    TFs, Targets = plan["TFs"], plan["Targets"]
+    M = np.zeros((len(TFs), len(Targets)))           # the skipped g_a == g_b entries: NaN -> 0 by fillna (Scribe.py:137)
+    M[plan["aa"], plan["bb"]] = np.where(np.isnan(vals), 0.0, vals)
+    adata.uns['causal_net'] = {"RDI": pd.DataFrame(M, index=TFs, columns=Targets)}
     return adata if copy else None
 
 
 def CLR(causality_mat, zscore_both_dim=None):
-    """Context likelihood of relatedness of a causality matrix (Scribe.py:142-176)."""
+    """Context likelihood of relatedness of a causality matrix (Scribe.py:142-176), computed on the GPU
+    (scribe_clr: row / column statistics and the element-wise z-scores are three small kernels over the matrix).
+    Keeps the reference's quirk for square input: the (n,) row statistics are broadcast along the last axis, so entry
+    (i, j) is z-scored against row j (Scribe.py:151-154)."""
     zscore_both_dim = check_symmetric(causality_mat) if zscore_both_dim is None else zscore_both_dim
     if isinstance(causality_mat, pd.DataFrame):
         mat = causality_mat.values
@@ -134,25 +186,7 @@ def CLR(causality_mat, zscore_both_dim=None):
         mat = causality_mat.toarray()
     else:
         mat = causality_mat
-    square = mat.shape[0] == mat.shape[1]
-
-    def zscore(axis):
-        z = np.round(mat, 10)
-        mu = np.mean(mat, axis=axis)
-        sd = np.std(mat, axis=axis, ddof=CLR_DDOF)
-        if not square:
-            mu = mu[:, None] if axis == 1 else mu[None, :]
-            sd = sd[:, None] if axis == 1 else sd[None, :]
-        z = np.divide(np.subtract(z, mu), sd)
-        z[z < 0] = 0
-        return z
-
-    z_row = zscore(1)
-    if zscore_both_dim:
-        z_col = zscore(0)
-        res = np.sqrt((np.square(z_row) + np.square(z_col)) / 2)
-    else:
-        res = np.sqrt(np.square(z_row))
+    res = _lib.default_handle().clr(np.asarray(mat, dtype=np.float64), bool(zscore_both_dim))
     if isinstance(causality_mat, pd.DataFrame):
         res = pd.DataFrame(res)
         res.index, res.columns = causality_mat.index, causality_mat.columns

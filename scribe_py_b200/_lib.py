@@ -49,8 +49,9 @@ _lib_lock = threading.Lock()
 # every symbol include/scribe_b200.h declares
 EXPORTS = [
     "scribe_abi_version", "scribe_last_error", "scribe_create", "scribe_destroy", "scribe_device_info",
-    "scribe_get_stats", "scribe_estimate", "scribe_debug_counts", "scribe_upload_matrix", "scribe_lagged_jobs",
-    "scribe_lagged_jobs_dev", "scribe_mi_jobs", "scribe_upload_coupling", "scribe_coupling_jobs", "scribe_coupling_jobs_dev",
+    "scribe_get_stats", "scribe_device_index", "scribe_estimate", "scribe_debug_counts", "scribe_upload_matrix", "scribe_lagged_jobs",
+    "scribe_lagged_jobs_dev", "scribe_mi_jobs", "scribe_upload_coupling", "scribe_upload_coupling_raw", "scribe_read_coupling_row", "scribe_coupling_jobs", "scribe_coupling_jobs_dev",
+    "scribe_clr", "scribe_top_edges", "scribe_roc",
 ]
 
 
@@ -72,6 +73,7 @@ def load_library():
         lib.scribe_destroy.restype = None
         lib.scribe_device_info.argtypes = [P, C.POINTER(I32), C.POINTER(I32), C.POINTER(I64), C.c_char_p, I32]
         lib.scribe_get_stats.argtypes = [P, C.POINTER(Stats)]
+        lib.scribe_device_index.argtypes = [P]
         lib.scribe_estimate.argtypes = [P, P, P, P, I64, I32, I32, I32, C.POINTER(Opts), D]
         lib.scribe_debug_counts.argtypes = [P, P, P, P, I64, I32, I32, I32, C.POINTER(Opts), P, P, P, P]
         lib.scribe_upload_matrix.argtypes = [P, P, I64, I64, P, I32]
@@ -79,8 +81,13 @@ def load_library():
         lib.scribe_lagged_jobs_dev.argtypes = [P, P, I64, C.POINTER(Opts), I32, P, P]
         lib.scribe_mi_jobs.argtypes = [P, P, P, I64, C.POINTER(Opts), P]
         lib.scribe_upload_coupling.argtypes = [P, P, P, I64, I64]
+        lib.scribe_upload_coupling_raw.argtypes = [P, P, P, I64, I64, I32, I32, C.POINTER(I32)]
+        lib.scribe_read_coupling_row.argtypes = [P, I32, I64, P]
         lib.scribe_coupling_jobs.argtypes = [P, P, P, I64, I32, C.POINTER(Opts), P, P]
         lib.scribe_coupling_jobs_dev.argtypes = [P, P, P, I64, I32, C.POINTER(Opts), P, P]
+        lib.scribe_clr.argtypes = [P, P, I64, I64, I32, P]
+        lib.scribe_top_edges.argtypes = [P, P, I64, I64, P, P, P, C.POINTER(I64)]
+        lib.scribe_roc.argtypes = [P, P, P, I64, D, P, P]
         _lib = lib
         return lib
 
@@ -136,6 +143,7 @@ class Handle:
         self._lib.scribe_device_info(h, C.byref(sm), C.byref(clk), C.byref(mem), name, 128)
         self.sm_count, self.clock_khz, self.mem_bytes = sm.value, clk.value, mem.value
         self.device_name = name.value.decode()
+        self.device = int(self._lib.scribe_device_index(h))          # CUDA ordinal: collectives must run on the same GPU
 
     def close(self):
         if getattr(self, "_h", None):
@@ -229,6 +237,26 @@ class Handle:
         if rc != SCRIBE_OK:
             _raise(rc)
 
+    def upload_coupling_raw(self, t0_layer, t1_layer, normalize=True, y_is_sum=True):
+        """Raw cells x genes layers -> resident normalised S / Y (device normalisation).  Returns False when the t0 layer
+        holds NaN (pandas would skip them in the mean): the caller must then take the host path."""
+        a = np.ascontiguousarray(t0_layer, dtype=np.float64)
+        b = np.ascontiguousarray(t1_layer, dtype=np.float64)
+        assert a.shape == b.shape and a.ndim == 2
+        flag = C.c_int32(0)
+        rc = self._lib.scribe_upload_coupling_raw(self._h, _ptr(a), _ptr(b), a.shape[0], a.shape[1], int(bool(normalize)),
+                                                  int(bool(y_is_sum)), C.byref(flag))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return flag.value == 0
+
+    def read_coupling_row(self, which, gene, n_cells):
+        out = np.empty(n_cells)
+        rc = self._lib.scribe_read_coupling_row(self._h, int(which), int(gene), _ptr(out))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return out
+
     def coupling_jobs(self, src, dst, opts, drop_zero_cells=True, out_dev_ptr=None, want_n_eff=False):
         src = np.ascontiguousarray(src, dtype=np.int32)
         dst = np.ascontiguousarray(dst, dtype=np.int32)
@@ -245,6 +273,42 @@ class Handle:
         if rc != SCRIBE_OK:
             _raise(rc)
         return (out, neff) if want_n_eff else out
+
+
+    # ---- consumers of the causal matrix ----------------------------------------------------------------
+    def clr(self, M, both_dims):
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        out = np.empty_like(M)
+        rc = self._lib.scribe_clr(self._h, _ptr(M), M.shape[0], M.shape[1], int(bool(both_dims)), _ptr(out))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return out
+
+    def top_edges(self, M, n_top):
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        assert M.ndim == 2 and M.shape[0] == M.shape[1]
+        n_top = int(min(n_top, M.size))
+        src = np.empty(n_top, dtype=np.int32); dst = np.empty(n_top, dtype=np.int32); w = np.empty(n_top)
+        found = C.c_int64(0)
+        rc = self._lib.scribe_top_edges(self._h, _ptr(M), M.shape[0], n_top, _ptr(src), _ptr(dst), _ptr(w), C.byref(found))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        k = found.value
+        return src[:k], dst[:k], w[:k]
+
+    def roc(self, scores, truth):
+        scores = np.ascontiguousarray(scores, dtype=np.float64)
+        truth = np.ascontiguousarray(truth, dtype=np.uint8)
+        n = scores.shape[0]
+        m = n * (n - 1) - int(np.isnan(scores[~np.eye(n, dtype=bool)]).sum())
+        x = np.empty(m + 1); y = np.empty(m + 1)
+        a = C.c_double()
+        rc = self._lib.scribe_roc(self._h, _ptr(scores), _ptr(truth), n, C.byref(a), _ptr(x), _ptr(y))
+        if rc == E_DOMAIN:
+            raise ZeroDivisionError(load_library().scribe_last_error().decode())
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return a.value, x, y
 
 
 _default = {}

@@ -198,6 +198,37 @@ class causal_model(object):
             out[d] = (sx, sy, sz)
         return out
 
+    @staticmethod
+    def _crdi_scales(E, run_off, jobs, L):
+        """Per-job np.std of the x, y and z arrays of differential-mode cRDI (cmi/cumi(..., normalization=True),
+        causal_network.py:219-221 -> information_estimators.py:150-153): x = e_a[tau-d : tau-d+n], y = e_b[tau-1+t] - e_b[tau+t]
+        (:271), z = the whole (N, L+1) block [cond[L-1] | ... | cond[0] | e_b[tau-1 : tau-1+n]] (:267-278), runs concatenated.
+        The slices of a job depend on few keys ((gene, offset, tau) / (target, tau) / (target, tau, conditioning set)), so the
+        standard deviations are cached by key: every source of a target that is outside its top set shares them."""
+        nr = len(run_off) - 1
+        runs = [(int(run_off[r]), int(run_off[r + 1])) for r in range(nr)]
+
+        def col(g, shift, tau):
+            return np.concatenate([E[g, a + shift:b - tau + shift] for a, b in runs if b - a > tau])
+
+        cx, cy, cz = {}, {}, {}
+        out = np.empty((len(jobs), 3))
+        for j in range(len(jobs)):
+            jb = jobs[j]
+            a, b, d = int(jb["src"]), int(jb["dst"]), int(jb["delay"])
+            cg = [int(v) for v in jb["cond_gene"][:L]]; cd = [int(v) for v in jb["cond_delay"][:L]]
+            tau = max([d] + cd)
+            kx, ky, kz = (a, tau - d, tau), (b, tau), (b, tau, tuple(cg), tuple(cd))
+            if kx not in cx:
+                cx[kx] = np.std(col(a, tau - d, tau)[:, None])
+            if ky not in cy:
+                cy[ky] = np.std((col(b, tau - 1, tau) - col(b, tau, tau))[:, None])
+            if kz not in cz:
+                cols = [col(cg[i], tau - cd[i], tau) for i in range(L - 1, -1, -1)] + [col(b, tau - 1, tau)]
+                cz[kz] = np.std(np.stack(cols, axis=1))
+            out[j, 0], out[j, 1], out[j, 2] = cx[kx], cy[ky], cz[kz]
+        return out
+
     def _frame(self, M, node_ids):
         ix = getattr(self, "_ix_cache", None)
         if ix is None or len(ix[0]) != len(node_ids) or ix[0] != node_ids:      # build the label Index once per gene list
@@ -234,10 +265,11 @@ class causal_model(object):
         jobs, scales = plan["jobs"], plan["scales"]
         opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
 
-        def evaluate(lo, hi):
-            return h.lagged_jobs(jobs[lo:hi], opts, differential_mode, None if scales is None else scales[lo:hi])
+        def evaluate(lo, hi, out_dev_ptr=None):
+            return h.lagged_jobs(jobs[lo:hi], opts, differential_mode, None if scales is None else scales[lo:hi],
+                                 out_dev_ptr=out_dev_ptr)
 
-        return _dist.sharded_evaluate(len(jobs), evaluate)
+        return _dist.sharded_evaluate(len(jobs), evaluate, h)
 
     # ------------------------------------------------------------------ RDI
     def rdi(self, delays, number_of_processes=1, uniformization=False, differential_mode=False):
@@ -298,18 +330,16 @@ class causal_model(object):
                 keep_own = [s_ for s_ in range(L + 1) if s_ != s_own]
                 jobs["cond_gene"][row, :L] = slot_gene[keep_own]; jobs["cond_delay"][row, :L] = slot_delay[keep_own]
             j += G - 1
+        scales = self._crdi_scales(E, run_off, jobs, L) if differential_mode else None
         h = _lib.default_handle()
         h.upload_matrix(E, run_off)
         opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
-        scales = None
-        if differential_mode:
-            raise NotImplementedError("differential_mode cRDI has no runnable reference (causal_network.py:250,:271 "
-                                      "slice one element too many)")
 
-        def evaluate(lo, hi):
-            return h.lagged_jobs(jobs[lo:hi], opts, False, scales)
+        def evaluate(lo, hi, out_dev_ptr=None):
+            return h.lagged_jobs(jobs[lo:hi], opts, differential_mode, None if scales is None else scales[lo:hi],
+                                 out_dev_ptr=out_dev_ptr)
 
-        vals = _dist.sharded_evaluate(len(jobs), evaluate)
+        vals = _dist.sharded_evaluate(len(jobs), evaluate, h)
         M = np.full((G, G), np.nan)
         M[jobs["src"], jobs["dst"]] = vals
         self.crdi_results = self._frame(M, node_ids)
@@ -376,24 +406,21 @@ class causal_model(object):
 
     # ------------------------------------------------------------------ evaluation (pass-through)
     def roc(self, results, true_graph_path):
-        """ROC curve and AUROC of a score matrix against an edge list file (causal_network.py:337-389)."""
+        """ROC curve and AUROC of a score matrix against an edge-list file (causal_network.py:337-389): every ordered pair of
+        node_ids, ranked by descending score (stable: ties keep source-major order), true / false positive counts along the
+        ranking normalised by their totals, trapezoid area.  The ranking, the cumulative counts and the area run on the GPU
+        (scribe_roc); the file parsing stays on the host.  Raises ZeroDivisionError, like the reference, when the ranking holds
+        no true or no false edge."""
         with open(true_graph_path) as fh:
             true_edges = set(line.strip().lower() for line in fh)
-        scored = []
-        for a in self.node_ids:
-            for b in self.node_ids:
-                if a == b:
-                    continue
-                scored.append((a.lower() + "\t" + b.lower(), results.loc[a, b]))
-        order = [e for e, _ in sorted(scored, key=lambda t: t[1], reverse=True)]
-        fp, tp = [0], [0]
-        for e in order:
-            hit = e in true_edges
-            tp.append(tp[-1] + (1 if hit else 0))
-            fp.append(fp[-1] + (0 if hit else 1))
-        x = [v / float(max(fp)) for v in fp]
-        y = [v / float(max(tp)) for v in tp]
-        auroc = 0
-        for i in range(1, len(x)):
-            auroc += abs((x[i] - x[i - 1]) * (y[i] + y[i - 1]) / 2)
-        return auroc, x, y
+        ids = list(self.node_ids)
+        low = [str(a).lower() for a in ids]
+        scores = self.__square(results, ids)
+        G = len(ids)
+        truth = np.zeros((G, G), dtype=np.uint8)
+        for i, a in enumerate(low):
+            for j, b in enumerate(low):
+                if i != j and (a + "\t" + b) in true_edges:
+                    truth[i, j] = 1
+        auroc, x, y = _lib.default_handle().roc(scores, truth)
+        return auroc, list(x), list(y)

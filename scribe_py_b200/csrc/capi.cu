@@ -4,7 +4,9 @@
 #include "../../include/scribe_b200.h"
 #include "kernels.cuh"
 #include "sweep_window.cuh"
+#include "prep.cuh"
 #include <cub/device/device_segmented_radix_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -57,7 +59,10 @@ struct scribe_handle {
     // workspaces
     DevBuf psi; int psi_n = 0;
     DevBuf jobs, partial, cols, specs, u, r, eps, cnt, wsum, out, flag, idx32a, idx32b, neff, dims, pjobs, single;
-    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, xsorted, permE, sortedE, rawjobs;
+    DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, permE, sortedE, rawjobs;
+    DevBuf post[8];                              // CLR / edge ranking / roc scratch
+    DevBuf raw0, raw1, stat, nanflag;            // raw layers / row statistics of the on-device normalisation
+    DevBuf sorted, rankf, crank, sortedS, rankS, permY, sortedY, rankY, rankE;   // rank-space count pass: ascending values + float ranks
     bool sortE_valid = false;             // permE / sortedE describe the uploaded expression matrix
     scribe_stats st{};
     size_t ws_budget = (size_t)3 << 30;   // per-chunk workspace target (bytes)
@@ -214,7 +219,7 @@ KdeSweepFn pick_kde_sweep(int dp) {
 // or pre-sorted columns)
 bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
     const int kcap = (o->k + 1 <= 6) ? 6 : ((o->k + 1 <= 16) ? 16 : 0);
-    if (o->estimator == SCRIBE_EST_MI) {                   // windowed sweep only (sorted by y; JobDesc.xsorted for the x marginal)
+    if (o->estimator == SCRIBE_EST_MI) {                   // windowed sweep only (sorted by y; JobDesc.srt[0] for the x marginal)
         if (!kcap || !pick_sweepw(dx, dy, 0, kcap, false)) return false;
         return o->path == SCRIBE_PATH_SWEEP || (o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N);
     }
@@ -225,48 +230,60 @@ bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
 }
 
 // argsort of n_seg key segments laid out [n_seg][stride] (segment s has len[s] valid items): perm_out[s][r] = index
-// of the r-th smallest key of segment s.  One cub::DeviceSegmentedRadixSort over all segments.
+// of the r-th smallest key of segment s; sorted_out (optional, default h->keys_out) receives the keys in ascending order and
+// rank_out (optional) the inverse permutation as float.  One cub::DeviceSegmentedRadixSort over all segments.
 void sort_segments(scribe_handle* h, const double* keys_in, int n_seg, int64_t stride, const std::vector<int>& len,
-                   int32_t* perm_out)
+                   int32_t* perm_out, double* sorted_out = nullptr, float* rank_out = nullptr, const std::vector<int>* only = nullptr)
 {
+    // `only`: sort just these of the n_seg columns (outputs keep the [n_seg][stride] layout; the other columns are left untouched)
     const int64_t total = (int64_t)n_seg * stride;
     if (total >= (int64_t)1 << 31) fail(SCRIBE_E_ARG, "sort too large for one chunk");
-    h->keys_out.ensure(sizeof(double) * total);
+    if (!sorted_out) { h->keys_out.ensure(sizeof(double) * total); sorted_out = h->keys_out.as<double>(); }
     h->vals_in.ensure(sizeof(int32_t) * total);
-    std::vector<int> off(2 * (size_t)n_seg);
-    for (int s = 0; s < n_seg; s++) { off[s] = (int)(s * stride); off[n_seg + s] = (int)(s * stride) + len[s]; }
+    const int n_sort = only ? (int)only->size() : n_seg;
+    std::vector<int> off(2 * (size_t)n_sort);
+    for (int i = 0; i < n_sort; i++) {
+        const int s = only ? (*only)[i] : i;
+        off[i] = (int)(s * stride); off[n_sort + i] = (int)(s * stride) + len[s];
+    }
+    if (n_sort == 0) return;
     h->seg_off.ensure(sizeof(int) * off.size());
     CU(cudaMemcpyAsync(h->seg_off.p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, h->stream));
     h->st.h2d_bytes += sizeof(int) * off.size();
     iota_segments_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 65535), 256, 0, h->stream>>>(h->vals_in.as<int32_t>(), stride, n_seg);
     CU(cudaGetLastError());
     size_t tmp = 0;
-    const int* b = h->seg_off.as<int>(); const int* e = b + n_seg;
-    CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, keys_in, h->keys_out.as<double>(), h->vals_in.as<int32_t>(), perm_out,
-                                                (int)total, n_seg, b, e, 0, 64, h->stream));
+    const int* b = h->seg_off.as<int>(); const int* e = b + n_sort;
+    CU(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, keys_in, sorted_out, h->vals_in.as<int32_t>(), perm_out,
+                                                (int)total, n_sort, b, e, 0, 64, h->stream));
     h->sort_tmp.ensure(tmp + 16);
-    CU(cub::DeviceSegmentedRadixSort::SortPairs(h->sort_tmp.p, tmp, keys_in, h->keys_out.as<double>(), h->vals_in.as<int32_t>(), perm_out,
-                                                (int)total, n_seg, b, e, 0, 64, h->stream));
-    CU(cudaStreamSynchronize(h->stream));         // `off` must outlive the copy; also surfaces sort errors here
+    CU(cub::DeviceSegmentedRadixSort::SortPairs(h->sort_tmp.p, tmp, keys_in, sorted_out, h->vals_in.as<int32_t>(), perm_out,
+                                                (int)total, n_sort, b, e, 0, 64, h->stream));
     h->st.kernel_launches += 2;
-}
-
-// argsort of the key columns `keyspec` (indices into h->cols, stride doubles apart) -> h->perm [keyspec.size()][stride]
-void argsort_key_columns(scribe_handle* h, const std::vector<int>& keyspec, const std::vector<int>& keylen, int64_t stride)
-{
-    const int64_t nk = (int64_t)keyspec.size();
-    h->keys_in.ensure(sizeof(double) * nk * stride);
-    h->perm.ensure(sizeof(int32_t) * nk * stride);
-    h->keyspecs.ensure(sizeof(int) * nk);
-    CU(cudaMemcpyAsync(h->keyspecs.p, keyspec.data(), sizeof(int) * nk, cudaMemcpyHostToDevice, h->stream));
-    for (int64_t k0 = 0; k0 < nk; k0 += 65535) {          // key columns -> one contiguous block (gridDim.y limit)
-        dim3 grid((unsigned)std::min<int64_t>((stride + TPB - 1) / TPB, 32), (unsigned)std::min<int64_t>(65535, nk - k0));
-        select_columns_kernel<<<grid, TPB, 0, h->stream>>>(h->cols.as<double>(), h->keyspecs.as<int>() + k0, stride,
-                                                           h->keys_in.as<double>() + (size_t)k0 * stride);
+    if (rank_out) {
+        if (only) fail(SCRIBE_E_STATE, "ranks need every column sorted");
+        rank_from_perm_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 65535), 256, 0, h->stream>>>(perm_out, b, e, stride, n_seg, rank_out);
         CU(cudaGetLastError());
         h->st.kernel_launches++;
     }
-    sort_segments(h, h->keys_in.as<double>(), (int)nk, stride, keylen, h->perm.as<int32_t>());
+    CU(cudaStreamSynchronize(h->stream));         // `off` must outlive the copy; also surfaces sort errors here
+}
+
+// every column of h->cols [n_cols][stride] (column c has len[c] valid items) in ascending order: h->sorted (values),
+// h->perm (argsort), h->rankf (inverse argsort as float).  The sweep order of a job is the perm of its key column; the
+// rank-space count pass reads sorted/rankf of its other columns.
+constexpr bool kRankPass = SWEEPW_RANK != 0;         // the windowed sweep's count pass works on ranks: every column is sorted, not only the keys
+
+void sort_all_columns(scribe_handle* h, int64_t n_cols, const std::vector<int>& len, int64_t stride, const std::vector<int>& key_cols)
+{
+    h->sorted.ensure(sizeof(double) * n_cols * stride);
+    h->perm.ensure(sizeof(int32_t) * n_cols * stride);
+    if (kRankPass) {
+        h->rankf.ensure(sizeof(float) * n_cols * stride);
+        sort_segments(h, h->cols.as<double>(), (int)n_cols, stride, len, h->perm.as<int32_t>(), h->sorted.as<double>(), h->rankf.as<float>());
+    } else {                                         // FP64 count pass: only the sweep order of the key columns is needed
+        sort_segments(h, h->cols.as<double>(), (int)n_cols, stride, len, h->perm.as<int32_t>(), h->sorted.as<double>(), nullptr, &key_cols);
+    }
 }
 
 using KdeFn = void (*)(const JobDesc*, int, const int*, double, double*);
@@ -555,16 +572,13 @@ void single_job(scribe_handle* h, const double* x, const double* y, const double
     h->out.ensure(sizeof(double));
     bool dom = false;
     bool ordered = false;
-    if (want_sweep(o, dx, dy, dz, (int)n)) {                 // argsort of the last column (last conditioning column; y for mi)
-        h->perm.ensure(sizeof(int32_t) * n);
-        if (dz == 0) {                                       // mi: x in ascending order for its marginal count
-            sort_segments(h, hj[0].col[0], 1, n, std::vector<int>{(int)n}, h->perm.as<int32_t>());
-            h->xsorted.ensure(sizeof(double) * n);
-            CU(cudaMemcpyAsync(h->xsorted.p, h->keys_out.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
-            hj[0].xsorted = h->xsorted.as<double>();
+    if (want_sweep(o, dx, dy, dz, (int)n)) {                 // all D columns in ascending order: sweep order = the last one (y for mi)
+        h->sorted.ensure(sizeof(double) * D * n); h->perm.ensure(sizeof(int32_t) * D * n); h->rankf.ensure(sizeof(float) * D * n);
+        sort_segments(h, base, D, n, std::vector<int>((size_t)D, (int)n), h->perm.as<int32_t>(), h->sorted.as<double>(), h->rankf.as<float>());
+        hj[0].perm = h->perm.as<int32_t>() + (size_t)(D - 1) * n;
+        for (int c = 0; c < D - 1 && c < 4; c++) {
+            hj[0].srt[c] = h->sorted.as<double>() + (size_t)c * n; hj[0].rk[c] = h->rankf.as<float>() + (size_t)c * n; hj[0].srt_n[c] = (int)n;
         }
-        sort_segments(h, hj[0].col[D - 1], 1, n, std::vector<int>{(int)n}, h->perm.as<int32_t>());
-        hj[0].perm = h->perm.as<int32_t>();
         ordered = true;
     }
     run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom, ordered);
@@ -660,7 +674,7 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             for (int t = lay.n_delays; t < 8; t++) { lay.delays[t] = 0; lay.n_of[t] = 0; }
         }
         const int64_t ncols = 3 * G * lay.n_delays, nk = G * lay.n_delays;
-        if (eligible && (n_jobs < nk || (size_t)ncols * n_max * 8 > h->ws_budget / 2 || nk * n_max >= ((int64_t)1 << 31))) eligible = false;
+        if (eligible && (n_jobs < nk || (size_t)ncols * n_max * 8 > h->ws_budget / 2 || ncols * n_max >= ((int64_t)1 << 31))) eligible = false;
         if (eligible) {
             const int64_t stride = n_max;
             std::vector<ColSpec> specs((size_t)ncols);
@@ -689,10 +703,12 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
             h->st.h2d_bytes += sizeof(scribe_job) * n_jobs;
             tr.lap("fast: validate + gather");
             const bool ordered = want_sweep(o, 1, 1, 1, (int)n_max);
-            if (ordered) {                                    // argsort of every gene's z column (its own past), per delay
-                std::vector<int> keyspec((size_t)nk), keylen((size_t)nk);
-                for (int64_t kq = 0; kq < nk; kq++) { keyspec[kq] = (int)(kq * 3 + 2); keylen[kq] = lay.n_of[kq / G]; }
-                argsort_key_columns(h, keyspec, keylen, stride);
+            if (ordered) {                                    // every lagged column in ascending order: sweep order (z), rank windows (x, y)
+                std::vector<int> collen((size_t)ncols);
+                for (int64_t c = 0; c < ncols; c++) collen[c] = lay.n_of[c / (3 * G)];
+                std::vector<int> keys((size_t)nk);
+                for (int64_t kq = 0; kq < nk; kq++) keys[kq] = (int)(kq * 3 + 2);
+                sort_all_columns(h, ncols, collen, stride, keys);
             }
             tr.lap("fast: key select + argsort");
             for (int t = 0; t < lay.n_delays; t++) h->st.point_pairs += per_delay[t] * (int64_t)lay.n_of[t] * lay.n_of[t];
@@ -706,7 +722,8 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
                 h->jobs.ensure(sizeof(JobDesc) * nj);
                 build_rdi_jobs_kernel<<<(unsigned)((nj + TPB - 1) / TPB), TPB, 0, h->stream>>>(
                     reinterpret_cast<const RawJob*>(h->rawjobs.p) + p0, nj, h->jobs.as<JobDesc>(), h->cols.as<double>(), stride,
-                    ordered ? h->perm.as<int32_t>() : nullptr, (int)G, lay, n_max);
+                    ordered ? h->perm.as<int32_t>() : nullptr, (ordered && kRankPass) ? h->sorted.as<double>() : nullptr,
+                    (ordered && kRankPass) ? h->rankf.as<float>() : nullptr, (int)G, lay, n_max);
                 CU(cudaGetLastError());
                 h->st.kernel_launches++;
                 run_jobs(h, none, (int)n_max, 1, 1, 1, o, out_dev + p0, true, nullptr, nullptr, ordered, nj);
@@ -829,14 +846,23 @@ void lagged_jobs(scribe_handle* h, const scribe_job* jobs, int64_t n_jobs, const
         tr.lap("gather launch + col pointers");
         bool ordered = false;
         if (want_sweep(o, 1, 1, dz, n_max)) {
-            // one argsort per distinct key column (the target's own past, last z column): shared by every source gene
-            std::vector<int> slot(specs.size(), -1), keyspec, keylen;
+            // every distinct lagged column of the chunk is sorted once and shared by the jobs that read it: the key column
+            // (the target's own past, last z column) gives the sweep order, the others their rank windows
+            if ((int64_t)specs.size() * stride >= ((int64_t)1 << 31)) fail(SCRIBE_E_ARG, "chunk too large to sort");
+            std::vector<int> collen(specs.size(), 0);
+            for (int64_t j = 0; j < nj; j++)
+                for (int c = 0; c < D; c++) collen[colidx[j * D + c]] = hj[j].n;      // equal tau (part of the column key) => equal n
+            std::vector<int> keys; std::vector<char> is_key(specs.size(), 0);
+            for (int64_t j = 0; j < nj; j++) { const int kc = colidx[j * D + D - 1]; if (!is_key[kc]) { is_key[kc] = 1; keys.push_back(kc); } }
+            sort_all_columns(h, (int64_t)specs.size(), collen, stride, keys);
             for (int64_t j = 0; j < nj; j++) {
-                const int sp = colidx[j * D + D - 1];
-                if (slot[sp] < 0) { slot[sp] = (int)keyspec.size(); keyspec.push_back(sp); keylen.push_back(hj[j].n); }
+                hj[j].perm = h->perm.as<int32_t>() + (size_t)colidx[j * D + D - 1] * stride;
+                for (int c = 0; kRankPass && c < D - 1 && c < 4; c++) {
+                    hj[j].srt[c] = h->sorted.as<double>() + (size_t)colidx[j * D + c] * stride;
+                    hj[j].rk[c] = h->rankf.as<float>() + (size_t)colidx[j * D + c] * stride;
+                    hj[j].srt_n[c] = hj[j].n;
+                }
             }
-            argsort_key_columns(h, keyspec, keylen, stride);
-            for (int64_t j = 0; j < nj; j++) hj[j].perm = h->perm.as<int32_t>() + (size_t)slot[colidx[j * D + D - 1]] * stride;
             ordered = true;
         }
         tr.lap("key select + argsort");
@@ -863,16 +889,21 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
         if (src[j] < 0 || src[j] >= h->cg || dst[j] < 0 || dst[j] >= h->cg) fail(SCRIBE_E_ARG, "gene index out of range");
     begin_call(h);
     const int64_t N = h->cc;
-    const bool ordered = want_sweep(o, 1, 1, 1, (int)N);
-    if (ordered && !h->permS_valid) {                    // argsort every gene's S row once per upload
-        h->permS.ensure(sizeof(int32_t) * h->cg * N);
-        sort_segments(h, h->S.as<double>(), (int)h->cg, N, std::vector<int>((size_t)h->cg, (int)N), h->permS.as<int32_t>());
+    // the sweep needs every gene's rows sorted in one segmented pass; a matrix too large for that (genes x cells >= 2^31) takes
+    // the dense kernel instead of failing
+    const bool ordered = want_sweep(o, 1, 1, 1, (int)N) && h->cg * N < ((int64_t)1 << 31);
+    if (ordered && !h->permS_valid) {                    // every gene's S and Y row in ascending order, once per upload
+        const std::vector<int> len((size_t)h->cg, (int)N);
+        h->permS.ensure(sizeof(int32_t) * h->cg * N); h->sortedS.ensure(sizeof(double) * h->cg * N); h->rankS.ensure(sizeof(float) * h->cg * N);
+        h->permY.ensure(sizeof(int32_t) * h->cg * N); h->sortedY.ensure(sizeof(double) * h->cg * N); h->rankY.ensure(sizeof(float) * h->cg * N);
+        sort_segments(h, h->S.as<double>(), (int)h->cg, N, len, h->permS.as<int32_t>(), h->sortedS.as<double>(), kRankPass ? h->rankS.as<float>() : nullptr);
+        if (kRankPass) sort_segments(h, h->Y.as<double>(), (int)h->cg, N, len, h->permY.as<int32_t>(), h->sortedY.as<double>(), h->rankY.as<float>());
         h->permS_valid = true;
     }
     double* out_dev = out;
     if (!out_is_device) { h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1)); out_dev = h->out.as<double>(); }
     const bool strips = o->path == SCRIBE_PATH_STRIP;                                                 // 3 compacted columns + order (+ strip images)
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / ((strips ? 12 : 4) * N * 8))));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(262144, (int64_t)(h->ws_budget / ((strips ? 13 : 5) * N * 8))));
     h->idx32a.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->idx32b.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
     h->neff.ensure(sizeof(int32_t) * std::max<int64_t>(n_jobs, 1));
@@ -883,18 +914,27 @@ void coupling_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int
     for (int64_t pos = 0; pos < n_jobs; pos += chunk) {
         const int64_t nj = std::min(chunk, n_jobs - pos);
         h->cols.ensure(sizeof(double) * 3 * N * nj);
+        const bool ranked = ordered && kRankPass;
+        if (ranked) h->crank.ensure(sizeof(float) * 2 * N * nj);
         std::vector<JobDesc> hj(nj);
         for (int64_t j = 0; j < nj; j++) {
             std::memset(&hj[j], 0, sizeof(JobDesc));
             double* b = h->cols.as<double>() + (size_t)j * 3 * N;
             hj[j].col[0] = b; hj[j].col[1] = b + N; hj[j].col[2] = b + 2 * N;
             hj[j].n = (int)N; hj[j].qoff = j * N;
+            if (ranked) {                                // ranks of the kept cells among ALL cells of the source's S row / the target's Y row
+                float* r = h->crank.as<float>() + (size_t)j * 2 * N;
+                hj[j].rk[0] = r; hj[j].rk[1] = r + N;
+                hj[j].srt[0] = h->sortedS.as<double>() + (size_t)src[pos + j] * N; hj[j].srt[1] = h->sortedY.as<double>() + (size_t)dst[pos + j] * N;
+                hj[j].srt_n[0] = hj[j].srt_n[1] = (int)N;
+            }
         }
         h->jobs.ensure(sizeof(JobDesc) * nj);
         CU(cudaMemcpyAsync(h->jobs.p, hj.data(), sizeof(JobDesc) * nj, cudaMemcpyHostToDevice, h->stream));
         h->st.h2d_bytes += sizeof(JobDesc) * nj;
         coupling_prep_kernel<<<(unsigned)nj, TPB, 0, h->stream>>>(h->S.as<double>(), h->Y.as<double>(), N,
-            ordered ? h->permS.as<int32_t>() : nullptr, h->idx32a.as<int32_t>() + pos, h->idx32b.as<int32_t>() + pos, drop_zero, h->cols.as<double>(), N,
+            ordered ? h->permS.as<int32_t>() : nullptr, ranked ? h->rankS.as<float>() : nullptr, ranked ? h->rankY.as<float>() : nullptr,
+            ranked ? h->crank.as<float>() : nullptr, h->idx32a.as<int32_t>() + pos, h->idx32b.as<int32_t>() + pos, drop_zero, h->cols.as<double>(), N,
             h->jobs.as<JobDesc>(), h->neff.as<int32_t>() + pos);
         CU(cudaGetLastError());
         h->st.kernel_launches++;
@@ -927,11 +967,10 @@ void mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n
     h->out.ensure(sizeof(double) * std::max<int64_t>(n_jobs, 1));
     const int64_t N = h->n_cells;
     const bool ordered = want_sweep(o, 1, 1, 0, (int)N) && (int64_t)h->n_genes * N < ((int64_t)1 << 31);
-    if (ordered && !h->sortE_valid) {                    // every gene's row: argsort + sorted values, once per upload
-        h->permE.ensure(sizeof(int32_t) * h->n_genes * N);
-        h->sortedE.ensure(sizeof(double) * h->n_genes * N);
-        sort_segments(h, h->E.as<double>(), (int)h->n_genes, N, std::vector<int>((size_t)h->n_genes, (int)N), h->permE.as<int32_t>());
-        CU(cudaMemcpyAsync(h->sortedE.p, h->keys_out.p, sizeof(double) * h->n_genes * N, cudaMemcpyDeviceToDevice, h->stream));
+    if (ordered && !h->sortE_valid) {                    // every gene's row: argsort, sorted values and ranks, once per upload
+        h->permE.ensure(sizeof(int32_t) * h->n_genes * N); h->sortedE.ensure(sizeof(double) * h->n_genes * N); h->rankE.ensure(sizeof(float) * h->n_genes * N);
+        sort_segments(h, h->E.as<double>(), (int)h->n_genes, N, std::vector<int>((size_t)h->n_genes, (int)N), h->permE.as<int32_t>(),
+                      h->sortedE.as<double>(), h->rankE.as<float>());
         h->sortE_valid = true;
     }
     for (int64_t pos = 0; pos < n_jobs; pos += 262144) {
@@ -944,7 +983,10 @@ void mi_jobs(scribe_handle* h, const int32_t* src, const int32_t* dst, int64_t n
             hj[j].col[0] = h->E.as<double>() + (size_t)a * N;
             hj[j].col[1] = h->E.as<double>() + (size_t)b * N;
             hj[j].n = (int)N;
-            if (ordered) { hj[j].perm = h->permE.as<int32_t>() + (size_t)b * N; hj[j].xsorted = h->sortedE.as<double>() + (size_t)a * N; }
+            if (ordered) {
+                hj[j].perm = h->permE.as<int32_t>() + (size_t)b * N;
+                hj[j].srt[0] = h->sortedE.as<double>() + (size_t)a * N; hj[j].rk[0] = h->rankE.as<float>() + (size_t)a * N; hj[j].srt_n[0] = (int)N;
+            }
             h->st.point_pairs += N * N;
         }
         run_jobs(h, hj, (int)N, 1, 1, 0, o, h->out.as<double>() + pos, false, nullptr, nullptr, ordered);
@@ -987,7 +1029,10 @@ int scribe_create(int device, scribe_handle** out) {
         cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
         h->mem_bytes = p.totalGlobalMem;
         std::snprintf(h->name, sizeof(h->name), "%.127s", p.name);
-        if (p.major < 10) { delete h; cudaSetDevice(prev); fail(SCRIBE_E_CUDA, "scribe_b200 is built for sm_100a only"); }
+        if (p.major != 10 || p.minor != 0) {           // the library carries sm_100a SASS only: fail here, not at the first launch
+            delete h; cudaSetDevice(prev);
+            fail(SCRIBE_E_CUDA, "scribe_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(p.major) + std::to_string(p.minor));
+        }
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->ev_call0)); CU(cudaEventCreate(&h->ev_call1));
         CU(cudaEventCreate(&h->ev_k0)); CU(cudaEventCreate(&h->ev_k1));
@@ -1009,8 +1054,10 @@ void scribe_destroy(scribe_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
                       &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
-                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->xsorted, &h->permE, &h->sortedE, &h->rawjobs})
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->permE, &h->sortedE, &h->rawjobs,
+                      &h->raw0, &h->raw1, &h->stat, &h->nanflag, &h->sorted, &h->rankf, &h->crank, &h->sortedS, &h->rankS, &h->permY, &h->sortedY, &h->rankY, &h->rankE})
         b->release();
+    for (DevBuf& b : h->post) b.release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1024,6 +1071,8 @@ int scribe_device_info(scribe_handle* h, int32_t* sm_count, int32_t* clock_khz, 
     if (name && name_len > 0) std::snprintf(name, name_len, "%s", h->name);
     return SCRIBE_OK;
 }
+
+int scribe_device_index(scribe_handle* h) { return h ? h->device : -1; }
 
 int scribe_get_stats(scribe_handle* h, scribe_stats* out) {
     if (!h || !out) { g_err = "NULL argument"; return SCRIBE_E_ARG; }
@@ -1094,6 +1143,153 @@ int scribe_upload_coupling(scribe_handle* h, const double* S, const double* Y, i
         h->st.h2d_bytes = 2 * bytes;
         h->cg = n_genes; h->cc = n_cells; h->permS_valid = false;
         end_call(h);
+    });
+}
+
+// ---- consumers of the causal matrix ---------------------------------------------------------------
+namespace {
+// rank the n x n entries of M (host) by descending score; mode as in edge_keys_kernel.  Leaves the sorted linear indices in
+// h->post[3] and returns how many of them are valid edges (finite key).
+int64_t rank_edges(scribe_handle* h, const double* M_host, int64_t n, int mode)
+{
+    const int64_t total = n * n;
+    if (total >= ((int64_t)1 << 31)) fail(SCRIBE_E_ARG, "matrix too large");
+    h->post[0].ensure(sizeof(double) * total); h->post[1].ensure(sizeof(double) * total); h->post[2].ensure(sizeof(int32_t) * total);
+    h->post[3].ensure(sizeof(int32_t) * total); h->post[4].ensure(sizeof(double) * total);
+    CU(cudaMemcpyAsync(h->post[0].p, M_host, sizeof(double) * total, cudaMemcpyHostToDevice, h->stream));
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    edge_keys_kernel<<<grid, 256, 0, h->stream>>>(h->post[0].as<double>(), n, mode, h->post[1].as<double>(), h->post[2].as<int32_t>());
+    CU(cudaGetLastError());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->post[1].as<double>(), h->post[4].as<double>(), h->post[2].as<int32_t>(),
+                                       h->post[3].as<int32_t>(), (int)total, 0, 64, h->stream));
+    h->sort_tmp.ensure(tmp + 16);
+    CU(cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tmp, h->post[1].as<double>(), h->post[4].as<double>(), h->post[2].as<int32_t>(),
+                                       h->post[3].as<int32_t>(), (int)total, 0, 64, h->stream));
+    // valid edges = keys below +inf: count them on the host from the sorted keys' tail (binary search over a D2H copy is overkill
+    // for n^2 <= a few million: one pass)
+    std::vector<double> keys((size_t)total);
+    CU(cudaMemcpyAsync(keys.data(), h->post[4].p, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int64_t valid = std::lower_bound(keys.begin(), keys.end(), INFINITY) - keys.begin();
+    h->st.h2d_bytes += sizeof(double) * total; h->st.d2h_bytes += sizeof(double) * total; h->st.kernel_launches += 3;
+    return valid;
+}
+}  // namespace
+
+int scribe_clr(scribe_handle* h, const double* M, int64_t rows, int64_t cols, int32_t both_dims, double* out) {
+    return guarded(h, [&] {
+        if (!M || !out || rows < 1 || cols < 1) fail(SCRIBE_E_ARG, "empty matrix");
+        begin_call(h);
+        const int64_t total = rows * cols;
+        h->post[0].ensure(sizeof(double) * total); h->post[1].ensure(sizeof(double) * total);
+        h->post[2].ensure(sizeof(double) * 2 * rows); h->post[3].ensure(sizeof(double) * 2 * cols);
+        CU(cudaMemcpyAsync(h->post[0].p, M, sizeof(double) * total, cudaMemcpyHostToDevice, h->stream));
+        double* rs = h->post[2].as<double>(); double* cs = h->post[3].as<double>();
+        line_mean_std_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(h->post[0].as<double>(), rows, cols, 1, rs, rs + rows);
+        CU(cudaGetLastError());
+        if (both_dims) {
+            line_mean_std_kernel<<<(unsigned)((cols * 32 + 255) / 256), 256, 0, h->stream>>>(h->post[0].as<double>(), rows, cols, 0, cs, cs + cols);
+            CU(cudaGetLastError());
+        }
+        clr_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, h->stream>>>(
+            h->post[0].as<double>(), rows, cols, rs, rs + rows, cs, cs + cols, both_dims ? 1 : 0, rows == cols ? 1 : 0, h->post[1].as<double>());
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, h->post[1].p, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+        h->st.h2d_bytes = sizeof(double) * total; h->st.d2h_bytes = sizeof(double) * total; h->st.kernel_launches = both_dims ? 3 : 2;
+        end_call(h);
+    });
+}
+
+int scribe_top_edges(scribe_handle* h, const double* M, int64_t n, int64_t n_top, int32_t* src, int32_t* dst, double* weight, int64_t* n_found) {
+    return guarded(h, [&] {
+        if (!M || n < 1 || n_top < 0 || !n_found || (n_top > 0 && (!src || !dst || !weight))) fail(SCRIBE_E_ARG, "bad top-edges request");
+        begin_call(h);
+        const int64_t valid = rank_edges(h, M, n, 0);
+        const int64_t take = std::min(valid, n_top);
+        std::vector<int32_t> idx((size_t)take);
+        if (take > 0) CU(cudaMemcpyAsync(idx.data(), h->post[3].p, sizeof(int32_t) * take, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < take; i++) { src[i] = idx[i] / (int32_t)n; dst[i] = idx[i] % (int32_t)n; weight[i] = M[idx[i]]; }
+        *n_found = take;
+        end_call(h);
+    });
+}
+
+int scribe_roc(scribe_handle* h, const double* scores, const uint8_t* truth, int64_t n, double* auroc, double* fpr, double* tpr) {
+    return guarded(h, [&] {
+        if (!scores || !truth || n < 2 || !auroc) fail(SCRIBE_E_ARG, "bad roc request");
+        begin_call(h);
+        const int64_t m = rank_edges(h, scores, n, 1);                // ranked off-diagonal edges (NaN scores excluded)
+        if (m < 1) fail(SCRIBE_E_ARG, "no scored edges");
+        h->post[5].ensure((size_t)n * n); h->post[6].ensure(sizeof(int32_t) * 2 * (m + 1)); h->post[7].ensure(sizeof(double) * (3 * (m + 1) + 1));
+        CU(cudaMemcpyAsync(h->post[5].p, truth, (size_t)n * n, cudaMemcpyHostToDevice, h->stream));
+        int32_t* tp = h->post[6].as<int32_t>(); int32_t* fp = tp + (m + 1);
+        double* x = h->post[7].as<double>(); double* y = x + (m + 1); double* terms = y + (m + 1); double* area = terms + m;
+        roc_scan_kernel<<<1, 1024, 0, h->stream>>>(h->post[3].as<int32_t>(), h->post[5].as<unsigned char>(), m, tp, fp);
+        CU(cudaGetLastError());
+        int32_t tot[2];
+        CU(cudaMemcpyAsync(&tot[0], tp + m, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(&tot[1], fp + m, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (tot[0] == 0 || tot[1] == 0) fail(SCRIBE_E_DOMAIN, "float division by zero");     // max(true_positive) or max(false_positive) == 0 (:375-376)
+        roc_curve_kernel<<<(unsigned)std::min<int64_t>((m + 256) / 256, 148 * 8), 256, 0, h->stream>>>(tp, fp, m, x, y, terms);
+        CU(cudaGetLastError());
+        sequential_sum_kernel<<<1, 32, 0, h->stream>>>(terms, m, area);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(auroc, area, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (fpr) CU(cudaMemcpyAsync(fpr, x, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, h->stream));
+        if (tpr) CU(cudaMemcpyAsync(tpr, y, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, h->stream));
+        h->st.kernel_launches += 3; h->st.d2h_bytes += sizeof(double) * (2 * (m + 1) + 1);
+        end_call(h);
+    });
+}
+
+int scribe_upload_coupling_raw(scribe_handle* h, const double* t0_layer, const double* t1_layer, int64_t n_cells, int64_t n_genes,
+                               int32_t normalize, int32_t y_is_sum, int32_t* t0_has_nan) {
+    return guarded(h, [&] {
+        if (!t0_layer || !t1_layer || n_genes < 1 || n_cells < 1) fail(SCRIBE_E_ARG, "empty coupling layers");
+        if (n_cells > 2000000) fail(SCRIBE_E_ARG, "too many cells");
+        begin_call(h);
+        const size_t bytes = sizeof(double) * n_genes * n_cells;
+        h->raw0.ensure(bytes); h->raw1.ensure(bytes); h->S.ensure(bytes); h->Y.ensure(bytes);
+        h->stat.ensure(sizeof(double) * 4 * n_genes); h->nanflag.ensure(2 * sizeof(int));
+        CU(cudaMemsetAsync(h->nanflag.p, 0, 2 * sizeof(int), h->stream));
+        CU(cudaMemcpyAsync(h->raw0.p, t0_layer, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->raw1.p, t1_layer, bytes, cudaMemcpyHostToDevice, h->stream));
+        // cells x genes -> genes x cells; NaN of the t1 layer -> 0 (Scribe.py:101); a NaN in the t0 layer is reported, not handled
+        dim3 grid((unsigned)((n_genes + 31) / 32), (unsigned)((n_cells + 31) / 32));
+        transpose_kernel<<<grid, 256, 0, h->stream>>>(h->raw0.as<double>(), n_cells, n_genes, h->S.as<double>(), 0, h->nanflag.as<int>());
+        CU(cudaGetLastError());
+        transpose_kernel<<<grid, 256, 0, h->stream>>>(h->raw1.as<double>(), n_cells, n_genes, h->Y.as<double>(), 1, h->nanflag.as<int>() + 1);
+        CU(cudaGetLastError());
+        double* st = h->stat.as<double>();
+        if (normalize) {
+            row_mean_range_kernel<<<(unsigned)((n_genes + 63) / 64), 64, 0, h->stream>>>(h->S.as<double>(), n_genes, n_cells, st, st + n_genes);
+            CU(cudaGetLastError());
+            row_mean_range_kernel<<<(unsigned)((n_genes + 63) / 64), 64, 0, h->stream>>>(h->Y.as<double>(), n_genes, n_cells, st + 2 * n_genes, st + 3 * n_genes);
+            CU(cudaGetLastError());
+        }
+        coupling_normalise_kernel<<<(unsigned)std::min<int64_t>((n_genes * n_cells + 255) / 256, 148 * 16), 256, 0, h->stream>>>(
+            h->S.as<double>(), h->Y.as<double>(), n_genes, n_cells, st, st + n_genes, st + 2 * n_genes, st + 3 * n_genes, normalize ? 1 : 0, y_is_sum ? 1 : 0);
+        CU(cudaGetLastError());
+        int flags[2] = {0, 0};
+        CU(cudaMemcpyAsync(flags, h->nanflag.p, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (t0_has_nan) *t0_has_nan = flags[0];
+        h->st.h2d_bytes = 2 * bytes; h->st.d2h_bytes = sizeof(flags); h->st.kernel_launches = normalize ? 5 : 3;
+        h->cg = n_genes; h->cc = n_cells; h->permS_valid = false;
+        end_call(h);
+    });
+}
+
+int scribe_read_coupling_row(scribe_handle* h, int32_t which, int64_t gene, double* out_row) {
+    return guarded(h, [&] {
+        if (h->cg == 0) fail(SCRIBE_E_STATE, "no coupling matrices uploaded");
+        if (gene < 0 || gene >= h->cg || !out_row || (which != 0 && which != 1)) fail(SCRIBE_E_ARG, "bad row request");
+        const double* src = (which == 0 ? h->S.as<double>() : h->Y.as<double>()) + (size_t)gene * h->cc;
+        CU(cudaMemcpyAsync(out_row, src, sizeof(double) * h->cc, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
     });
 }
 

@@ -37,7 +37,10 @@ struct JobDesc {
     int32_t n;                // points
     int32_t pad;
     double absmax;            // windowed sweep: largest |coordinate| of the job, written on the device by job_absmax_kernel
-    const double* xsorted;    // windowed sweep for mi (no conditioning column): col[0] in ascending order (marginal count of x)
+    // windowed sweep, rank-space count pass: for every NON-key coordinate c (x, y, then the extra conditioning columns)
+    const double* srt[4];     //   the values of that coordinate in ascending order (srt_n[c] of them): the ball |q_c - v| <= eps is one
+    const float*  rk[4];      //   rank range of it; rk[c][row] = position of the job's row in that order (an integer < 2^22, as float)
+    int32_t srt_n[4];         //   (srt_n may exceed n: dynamics coupling ranks a job's kept cells among ALL cells of the gene)
 };
 
 struct PointOut {             // optional per-point outputs (debug entry point, generic path, kNN-only mode)
@@ -1524,6 +1527,18 @@ __global__ void iota_segments_kernel(int32_t* __restrict__ v, int64_t stride, in
         v[i] = (int32_t)(i % stride);
 }
 
+// rank[s][perm[s][p]] = p for p < len(s): the inverse of an argsort, as float (exact: p < 2^22)
+__global__ void rank_from_perm_kernel(const int32_t* __restrict__ perm, const int* __restrict__ seg_begin, const int* __restrict__ seg_end,
+                                      int64_t stride, int n_seg, float* __restrict__ rank)
+{
+    const int64_t total = stride * n_seg;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i / stride);
+        const int p = (int)(i - (int64_t)s * stride);
+        if (p < seg_end[s] - seg_begin[s]) rank[(size_t)s * stride + perm[i]] = (float)p;
+    }
+}
+
 // out[job] = (sum of that job's CTA partials, in CTA order) / n      (np.mean at :109,:173,:403)
 __global__ void finalize_mean_kernel(const JobDesc* __restrict__ jobs, const double* __restrict__ partial,
                                      int blocks_per_job, int n_jobs, double* __restrict__ out)
@@ -1770,14 +1785,15 @@ gather_lagged_kernel(const double* __restrict__ E, int64_t n_cells, const int64_
 // ------------------------------------------------------------------------------------------------
 // Descriptors of plain RDI jobs (no conditioning set, no per-job scaling) built on the device from the caller's job
 // table.  Column layout of the chunk: column ((di * G + gene) * 3 + role), role 0 = x (shift 0), 1 = y (shift d),
-// 2 = z (shift d-1), di = index of the job's delay in `delays`; sort order of the z columns: perm[(di * G + gene)].
+// 2 = z (shift d-1), di = index of the job's delay in `delays`; every column is sorted: perm / sorted / rank are laid out like cols.
 // ------------------------------------------------------------------------------------------------
 struct RdiLayout { int32_t n_delays; int32_t delays[8]; int32_t n_of[8]; };
 struct RawJob { int32_t src, dst, delay, n_cond; int32_t cond_gene[4]; int32_t cond_delay[4]; };   // == scribe_job
 
 __global__ void __launch_bounds__(TPB)
 build_rdi_jobs_kernel(const RawJob* __restrict__ raw, int64_t n_jobs, JobDesc* __restrict__ out, const double* __restrict__ cols,
-                      int64_t stride, const int32_t* __restrict__ perm, int n_genes, RdiLayout lay, int64_t n_max)
+                      int64_t stride, const int32_t* __restrict__ perm, const double* __restrict__ sorted, const float* __restrict__ rank,
+                      int n_genes, RdiLayout lay, int64_t n_max)
 {
     const int64_t j = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (j >= n_jobs) return;
@@ -1793,11 +1809,18 @@ build_rdi_jobs_kernel(const RawJob* __restrict__ raw, int64_t n_jobs, JobDesc* _
     jd.col[1] = cols + ((base + jb.dst) * 3 + 1) * stride;
     jd.col[2] = cols + ((base + jb.dst) * 3 + 2) * stride;
     jd.w = nullptr;
-    jd.perm = perm ? perm + (base + jb.dst) * stride : nullptr;
+    jd.perm = perm ? perm + ((base + jb.dst) * 3 + 2) * stride : nullptr;          // order of the key: the target's z column
     jd.strip = nullptr; jd.npad = 0;
     jd.qoff = j * n_max;
     jd.n = lay.n_of[di]; jd.pad = 0;
-    jd.absmax = 0.0; jd.xsorted = nullptr;
+    jd.absmax = 0.0;
+    #pragma unroll
+    for (int c = 0; c < 4; c++) { jd.srt[c] = nullptr; jd.rk[c] = nullptr; jd.srt_n[c] = 0; }
+    if (sorted) {                                    // rank-space count pass: x of the source, y of the target
+        jd.srt[0] = sorted + ((base + jb.src) * 3 + 0) * stride; jd.rk[0] = rank + ((base + jb.src) * 3 + 0) * stride;
+        jd.srt[1] = sorted + ((base + jb.dst) * 3 + 1) * stride; jd.rk[1] = rank + ((base + jb.dst) * 3 + 1) * stride;
+        jd.srt_n[0] = jd.srt_n[1] = lay.n_of[di];
+    }
     out[j] = jd;
 }
 
@@ -1818,6 +1841,9 @@ __global__ void set_weight_ptr_kernel(JobDesc* __restrict__ jobs, int64_t n_jobs
 __global__ void __launch_bounds__(TPB)
 coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y, int64_t n_cells,
                      const int32_t* __restrict__ permS,   // [G][n_cells]: cells of each gene sorted by S (or nullptr)
+                     const float* __restrict__ rankS,     // [G][n_cells]: rank of every cell in its gene's ascending S row (or nullptr)
+                     const float* __restrict__ rankY,     //               ... in its gene's ascending Y row
+                     float* __restrict__ crank,           // [jobs][2][col_stride]: ranks of the kept cells (x in S[src], y in Y[dst])
                      const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int drop_zero,
                      double* __restrict__ cols, int64_t col_stride, JobDesc* __restrict__ jobs, int32_t* __restrict__ n_eff)
 {
@@ -1830,16 +1856,22 @@ coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y,
     double* ox = cols + (size_t)job * 3 * col_stride;
     double* oy = ox + col_stride;
     double* oz = oy + col_stride;
+    float* orx = crank ? crank + (size_t)job * 2 * col_stride : nullptr;
+    float* ory = crank ? orx + col_stride : nullptr;
+    const float* rxs = rankS ? rankS + (size_t)src[job] * n_cells : nullptr;
+    const float* rys = rankY ? rankY + (size_t)dst[job] * n_cells : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) base_s = 0;
     __syncthreads();
     for (int64_t c0 = 0; c0 < n_cells; c0 += TPB) {
         const int64_t r = c0 + tid;                      // rank in the target's z-sorted order (or plain cell index)
         double x = 0, y = 0, z = 0;
+        float rx = 0.f, ry = 0.f;
         bool keep = false;
         if (r < n_cells) {
             const int64_t c = permS ? permS[(size_t)dst[job] * n_cells + r] : r;
             x = xs[c]; y = ys[c]; z = zs[c];
+            if (orx) { rx = rxs[c]; ry = rys[c]; }
             keep = drop_zero ? (__dadd_rn(__dadd_rn(x, y), z) > 0.0) : true;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -1850,6 +1882,7 @@ coupling_prep_kernel(const double* __restrict__ S, const double* __restrict__ Y,
         if (keep) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
             ox[pos] = x; oy[pos] = y; oz[pos] = z;
+            if (orx) { orx[pos] = rx; ory[pos] = ry; }
         }
         __syncthreads();
         if (tid == 0) { int t = 0; for (int w = 0; w < TPB / 32; w++) t += warp_cnt[w]; base_s += t; }

@@ -30,7 +30,11 @@ namespace scribe {
 #define SWEEPW_UNROLL 8
 #endif
 #ifndef SWEEPW_MERGED
-#define SWEEPW_MERGED 1                   // one marked-candidate loop for all query slots of a lane (0: one loop per slot)
+#define SWEEPW_MERGED 0                   // 1: one marked-candidate loop for all query slots of a lane.  Measured on B200 (r2): +1..3 % time, off
+#endif
+#ifndef SWEEPW_RANK
+#define SWEEPW_RANK 0                     // 1: pass 2 tests integer rank windows on the FP32/ALU pipes instead of FP64 differences (bit-identical;
+                                          // measured on B200, r2: +4 % time at N = 2000, -1.5 % on cumi at N = 20 000 -- see DESIGN.md)
 #endif
 #ifndef SWEEPW_MIN_CTAS
 #define SWEEPW_MIN_CTAS 10                // 102 registers: 20 resident warps per SM; measured equal at N = 2000 and 8 % faster at N = 20 000 than 12 CTAs / 80 registers
@@ -118,6 +122,54 @@ __device__ __forceinline__ void wball_zy(double dz0, double dz1, bool two, doubl
             " setp.le.and.f64 pz,a,%6,pz;\n setp.le.and.f64 py,c,%6,pz;\n"
             " @pz add.f64 %2,%2,%9;\n @pz or.b32 %0,%0,%8;\n @py add.f64 %3,%3,%9;\n @py or.b32 %1,%1,%8;\n}"
             : "+r"(bz), "+r"(by), "+d"(wz), "+d"(wyz) : "d"(dz0), "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w));
+}
+
+// ---- rank-space pass 2 -------------------------------------------------------------------------------------------------------
+// A ball |q_c - v| <= eps in one coordinate is a contiguous range [lo_c, hi_c] of that coordinate's ascending order (found by
+// binary search with the dense kernel's own subtraction, so it is the same set).  With centre m = (lo + hi) / 2 and half-width
+// h = (hi - lo) / 2 (half-integers, exact in FP32 below 2^22) a candidate of rank r is in the ball iff |r - m| <= h: one packed
+// FP32 subtract for two coordinates, one FSETP and one predicated OR per coordinate -- nothing on the FP64 pipe.
+__device__ __forceinline__ void rank_bit1(float d0, float h0, unsigned bit, unsigned& b0)
+{
+    asm("{\n .reg .pred p;\n .reg .f32 a0;\n abs.f32 a0,%1;\n setp.le.f32 p,a0,%2;\n @p or.b32 %0,%0,%3;\n}"
+        : "+r"(b0) : "f"(d0), "f"(h0), "r"(bit));
+}
+__device__ __forceinline__ void rank_bit2(float d0, float d1, float h0, float h1, unsigned bit, unsigned& b0, unsigned& b1)
+{
+    asm("{\n .reg .pred p,q;\n .reg .f32 a0,a1;\n abs.f32 a0,%2; abs.f32 a1,%3;\n setp.le.f32 p,a0,%4;\n setp.le.f32 q,a1,%5;\n"
+        " @p or.b32 %0,%0,%6;\n @q or.b32 %1,%1,%6;\n}"
+        : "+r"(b0), "+r"(b1) : "f"(d0), "f"(d1), "f"(h0), "f"(h1), "r"(bit));
+}
+// both extra conditioning columns inside -> one bit
+__device__ __forceinline__ void rank_bit_and2(float d0, float d1, float h0, float h1, unsigned bit, unsigned& b)
+{
+    asm("{\n .reg .pred p;\n .reg .f32 a0,a1;\n abs.f32 a0,%1; abs.f32 a1,%2;\n setp.le.f32 p,a0,%3;\n setp.le.and.f32 p,a1,%4,p;\n"
+        " @p or.b32 %0,%0,%5;\n}"
+        : "+r"(b) : "f"(d0), "f"(d1), "f"(h0), "f"(h1), "r"(bit));
+}
+// weighted (cumi), one conditioning column: y inside the key window -> by bit and W_yz += w
+__device__ __forceinline__ void rank_wy(float dy, float hy, double w, unsigned win, unsigned bit, unsigned& by, double& wyz)
+{
+    asm("{\n .reg .pred pin,p;\n .reg .b32 t;\n .reg .f32 a;\n and.b32 t,%4,%5;\n setp.ne.u32 pin,t,0;\n abs.f32 a,%2;\n"
+        " setp.le.and.f32 p,a,%3,pin;\n @p add.f64 %1,%1,%6;\n @p or.b32 %0,%0,%5;\n}"
+        : "+r"(by), "+d"(wyz) : "f"(dy), "f"(hy), "r"(win), "r"(bit), "d"(w));
+}
+// weighted, 2 or 3 conditioning columns: z-ball inside the key window -> bz bit, W_z += w; y inside it -> by bit, W_yz += w
+__device__ __forceinline__ void rank_wzy(float dz0, float hz0, float dz1, float hz1, bool two, float dy, float hy, double w, unsigned win,
+                                         unsigned bit, unsigned& bz, unsigned& by, double& wz, double& wyz)
+{
+    if (two)
+        asm("{\n .reg .pred pz,py;\n .reg .b32 t;\n .reg .f32 a,b,c;\n and.b32 t,%10,%11;\n setp.ne.u32 pz,t,0;\n abs.f32 a,%4; abs.f32 b,%6; abs.f32 c,%8;\n"
+            " setp.le.and.f32 pz,a,%5,pz;\n setp.le.and.f32 pz,b,%7,pz;\n setp.le.and.f32 py,c,%9,pz;\n"
+            " @pz add.f64 %2,%2,%12;\n @pz or.b32 %0,%0,%11;\n @py add.f64 %3,%3,%12;\n @py or.b32 %1,%1,%11;\n}"
+            : "+r"(bz), "+r"(by), "+d"(wz), "+d"(wyz)
+            : "f"(dz0), "f"(hz0), "f"(dz1), "f"(hz1), "f"(dy), "f"(hy), "r"(win), "r"(bit), "d"(w));
+    else
+        asm("{\n .reg .pred pz,py;\n .reg .b32 t;\n .reg .f32 a,c;\n and.b32 t,%8,%9;\n setp.ne.u32 pz,t,0;\n abs.f32 a,%4; abs.f32 c,%6;\n"
+            " setp.le.and.f32 pz,a,%5,pz;\n setp.le.and.f32 py,c,%7,pz;\n"
+            " @pz add.f64 %2,%2,%10;\n @pz or.b32 %0,%0,%9;\n @py add.f64 %3,%3,%10;\n @py or.b32 %1,%1,%9;\n}"
+            : "+r"(bz), "+r"(by), "+d"(wz), "+d"(wyz)
+            : "f"(dz0), "f"(hz0), "f"(dy), "f"(hy), "r"(win), "r"(bit), "d"(w));
 }
 
 // |v| without the FP64 pipe (fabs() of a value that feeds a select compiles to DADD -RZ,|v|)
@@ -431,34 +483,67 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         #pragma unroll
         for (int q = 0; q < Q; q++) { lo[q] = la[q]; hi[q] = ha[q] - 1; }
     }
-    int nxm[Q];                                                    // mi: marginal count of x over ALL points (incl. self)
-    #pragma unroll
-    for (int q = 0; q < Q; q++) nxm[q] = 0;
-    if constexpr (DZ == 0) {
-        const double* __restrict__ xs = jd.xsorted;                // col[0] ascending: the ball |x_i - x_j| <= eps is a rank range
+    // window of a query in an ascending column `sv` of m values: first / last index whose value is within eps of v
+    auto window_in = [&](const double* __restrict__ sv, int m, const double (&v)[Q], int (&wl)[Q], int (&wh)[Q]) {
         int la[Q], lb[Q], ha[Q], hb[Q];
         #pragma unroll
-        for (int q = 0; q < Q; q++) { la[q] = 0; lb[q] = n; ha[q] = 0; hb[q] = n; }
-        const int iters = 33 - __clz(n);
+        for (int q = 0; q < Q; q++) { la[q] = 0; lb[q] = m; ha[q] = 0; hb[q] = m; }
+        const int iters = 33 - __clz(m);
         for (int it = 0; it < iters; it++) {
             #pragma unroll
             for (int q = 0; q < Q; q++) {
                 if (la[q] < lb[q]) {
                     const int mid = (la[q] + lb[q]) >> 1;
-                    const double xr = xs[mid];
-                    const bool A = (xr > qc[q][0]) || (fabs(qc[q][0] - xr) <= eps[q]);
+                    const double xr = sv[mid];
+                    const bool A = (xr > v[q]) || (fabs(v[q] - xr) <= eps[q]);
                     if (A) lb[q] = mid; else la[q] = mid + 1;
                 }
                 if (ha[q] < hb[q]) {
                     const int mid = (ha[q] + hb[q]) >> 1;
-                    const double xr = xs[mid];
-                    const bool B = (xr < qc[q][0]) || (fabs(qc[q][0] - xr) <= eps[q]);
+                    const double xr = sv[mid];
+                    const bool B = (xr < v[q]) || (fabs(v[q] - xr) <= eps[q]);
                     if (B) ha[q] = mid + 1; else hb[q] = mid;
                 }
             }
         }
         #pragma unroll
-        for (int q = 0; q < Q; q++) nxm[q] = ha[q] - la[q];
+        for (int q = 0; q < Q; q++) { wl[q] = la[q]; wh[q] = ha[q] - 1; }
+    };
+    constexpr bool RANKED = SWEEPW_RANK != 0;
+    int nxm[Q];                                                    // mi: marginal count of x over ALL points (incl. self)
+    #pragma unroll
+    for (int q = 0; q < Q; q++) nxm[q] = 0;
+    float hw[Q][NPA];                                              // rank windows of the non-key coordinates: half-widths (centres go to qf2)
+    #pragma unroll
+    for (int q = 0; q < Q; q++)
+        #pragma unroll
+        for (int d = 0; d < NPA; d++) hw[q][d] = -1.f;
+    if constexpr (RANKED || DZ == 0) {
+        float ctr[Q][NPA];
+        #pragma unroll
+        for (int q = 0; q < Q; q++)
+            #pragma unroll
+            for (int d = 0; d < NPA; d++) ctr[q][d] = 0.f;
+        #pragma unroll
+        for (int c = 0; c < (RANKED ? NP : 1); c++) {
+            double v[Q]; int wl[Q], wh[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = qc[q][c];
+            window_in(jd.srt[c], jd.srt_n[c], v, wl, wh);
+            #pragma unroll
+            for (int q = 0; q < Q; q++) {
+                ctr[q][c] = 0.5f * (float)(wl[q] + wh[q]);         // exact: srt_n <= 2^21
+                hw[q][c]  = 0.5f * (float)(wh[q] - wl[q]);
+                if (DZ == 0 && c == 0) nxm[q] = wh[q] - wl[q] + 1;
+            }
+        }
+        if constexpr (RANKED) {
+            #pragma unroll
+            for (int q = 0; q < Q; q++)
+                #pragma unroll
+                for (int d = 0; d < NPA; d += 2)
+                    asm("mov.b64 %0, {%1,%2};" : "=l"(qf2[q][d / 2]) : "f"(ctr[q][d]), "f"(ctr[q][d + 1]));
+        }
     }
     int nxyz[Q], nxz[Q], nyz[Q], nz[Q];
     #pragma unroll
@@ -478,6 +563,31 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     #pragma unroll
     for (int q = 0; q < Q; q++) wyz[q] = wz[q] = 0.0;
 
+    // per-chunk epilogue shared by both forms of the scan: masks -> counts
+    auto tally = [&](int q, int base, unsigned zw, unsigned mx, unsigned my, unsigned mz) {
+        if (DZ == 0) {
+            nxz[q] += __popc(zw & mx);                             // n_xy: x-ball inside the y-window
+        } else if (!WEIGHTED) {
+            unsigned z = zw;
+            if (DZ > 1) { z &= mz; nz[q] += __popc(z); }
+            const unsigned xw = z & mx;
+            nxz[q]  += __popc(xw);
+            nyz[q]  += __popc(z & my);
+            nxyz[q] += __popc(xw & my);
+        } else {                                                   // my (and mz) already carry the window
+            const unsigned z = (DZ > 1) ? mz : zw;
+            if (DZ > 1) nz[q] += __popc(z);
+            nxz[q]  += __popc(z & mx);
+            nyz[q]  += __popc(my);
+            nxyz[q] += __popc(my & mx);
+            if (DZ == 1) {
+                const int a = max(lo[q] - base, 0), b = min(hi[q] - base, 31);
+                if (b >= a) wz[q] += bw[33 + b] - bw[32 + a];
+            }
+        }
+    };
+
+    // FP64 form (SWEEPW_RANK=0): coordinate differences against eps
     auto count_body = [&](auto q_first, int base) {
         constexpr int Q0 = decltype(q_first)::value;
         unsigned mx[Q], my[Q], mz[Q], zw[Q];
@@ -519,32 +629,109 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             for (int q = Q0; q < Q; q++) { mx[q] |= bx[q] << jb; my[q] |= by[q] << jb; if (DZ > 1) mz[q] |= bz[q] << jb; }
         }
         #pragma unroll
-        for (int q = Q0; q < Q; q++) {
-            if (DZ == 0) {
-                nxz[q] += __popc(zw[q] & mx[q]);                  // n_xy: x-ball inside the y-window
-            } else if (!WEIGHTED) {
-                unsigned z = zw[q];
-                if (DZ > 1) { z &= mz[q]; nz[q] += __popc(z); }
-                const unsigned xw = z & mx[q];
-                nxz[q]  += __popc(xw);
-                nyz[q]  += __popc(z & my[q]);
-                nxyz[q] += __popc(xw & my[q]);
-            } else {                                             // my (and mz) already carry the window
-                const unsigned z = (DZ > 1) ? mz[q] : zw[q];
-                if (DZ > 1) nz[q] += __popc(z);
-                nxz[q]  += __popc(z & mx[q]);
-                nyz[q]  += __popc(my[q]);
-                nxyz[q] += __popc(my[q] & mx[q]);
-                if (DZ == 1) {
-                    const int a = max(lo[q] - base, 0), b = min(hi[q] - base, 31);
-                    if (b >= a) wz[q] += bw[33 + b] - bw[32 + a];
+        for (int q = Q0; q < Q; q++) tally(q, base, zw[q], mx[q], my[q], mz[q]);
+    };
+
+    // rank form: the staged candidates are their ranks in the non-key columns (bf), the queries their window centres (qf2)
+    auto count_body_rank = [&](auto q_first, int base) {
+        constexpr int Q0 = decltype(q_first)::value;
+        unsigned mx[Q], my[Q], mz[Q], zw[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; zw[q] = range_mask(lo[q] - base, hi[q] - base); }
+        #pragma unroll 1
+        for (int jb = 0; jb < 32; jb += UNR) {
+            unsigned bx[Q], by[Q], bz[Q], zb[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; zb[q] = zw[q] >> jb; }
+            #pragma unroll
+            for (int t = 0; t < UNR; t++) {
+                const int j = jb + t;
+                unsigned long long cf2[NPA / 2];
+                if constexpr (NPA == 2) { cf2[0] = *reinterpret_cast<const unsigned long long*>(&bf[j][0]); }
+                else { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&bf[j][0]); cf2[0] = v.x; cf2[NPA / 2 - 1] = v.y; }
+                double wj_ = 0.0;
+                if (WEIGHTED) wj_ = bw[j];
+                const unsigned bit = 1u << t;
+                #pragma unroll
+                for (int q = Q0; q < Q; q++) {
+                    float df[NPA];
+                    #pragma unroll
+                    for (int d = 0; d < NPA; d += 2) {
+                        unsigned long long dd;
+                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(qf2[q][d / 2]), "l"(cf2[d / 2]));
+                        asm("mov.b64 {%0,%1}, %2;" : "=f"(df[d]), "=f"(df[d + 1]) : "l"(dd));
+                    }
+                    if constexpr (DZ == 0) {
+                        rank_bit1(df[0], hw[q][0], bit, bx[q]);
+                    } else if constexpr (!WEIGHTED) {
+                        rank_bit2(df[0], df[1], hw[q][0], hw[q][1], bit, bx[q], by[q]);
+                        if constexpr (DZ == 2) rank_bit1(df[NP > 2 ? 2 : 0], hw[q][NP > 2 ? 2 : 0], bit, bz[q]);
+                        if constexpr (DZ == 3) rank_bit_and2(df[NP > 2 ? 2 : 0], df[NP > 3 ? 3 : 0], hw[q][NP > 2 ? 2 : 0], hw[q][NP > 3 ? 3 : 0], bit, bz[q]);
+                    } else if constexpr (DZ == 1) {
+                        rank_bit1(df[0], hw[q][0], bit, bx[q]);
+                        rank_wy(df[1], hw[q][1], wj_, zb[q], bit, by[q], wyz[q]);
+                    } else if constexpr (DZ == 2) {
+                        rank_bit1(df[0], hw[q][0], bit, bx[q]);
+                        rank_wzy(df[NP > 2 ? 2 : 0], hw[q][NP > 2 ? 2 : 0], 0.f, 0.f, false, df[1], hw[q][1], wj_, zb[q], bit, bz[q], by[q], wz[q], wyz[q]);
+                    } else {
+                        rank_bit1(df[0], hw[q][0], bit, bx[q]);
+                        rank_wzy(df[NP > 2 ? 2 : 0], hw[q][NP > 2 ? 2 : 0], df[NP > 3 ? 3 : 0], hw[q][NP > 3 ? 3 : 0], true, df[1], hw[q][1], wj_, zb[q], bit,
+                                 bz[q], by[q], wz[q], wyz[q]);
+                    }
                 }
             }
+            #pragma unroll
+            for (int q = Q0; q < Q; q++) { mx[q] |= bx[q] << jb; my[q] |= by[q] << jb; if (DZ > 1) mz[q] |= bz[q] << jb; }
         }
+        #pragma unroll
+        for (int q = Q0; q < Q; q++) tally(q, base, zw[q], mx[q], my[q], mz[q]);
+    };
+
+    // candidates of the rank form: ranks of the NP non-key coordinates (NaN beyond n: never inside a window) and the weight
+    struct RChunk { float r[NPA]; double w; };
+    auto load_rchunk = [&](int chunk) {
+        RChunk c;
+        const int rank = chunk * 32 + lane;
+        const bool ok = rank < n;
+        const int idx = ok ? (perm ? perm[rank] : rank) : 0;
+        #pragma unroll
+        for (int d = 0; d < NPA; d++) c.r[d] = (ok && d < NP) ? jd.rk[d < NP ? d : 0][idx] : __int_as_float(0x7fc00000);
+        c.w = 0.0;
+        if (WEIGHTED) c.w = ok ? jd.w[idx] : 0.0;
+        return c;
+    };
+    auto stage_r = [&](const RChunk& c) {
+        __syncwarp();
+        #pragma unroll
+        for (int d = 0; d < NPA; d += 2) { float2 v; v.x = c.r[d]; v.y = c.r[d + 1]; *reinterpret_cast<float2*>(&bf[lane][d]) = v; }
+        if (WEIGHTED) {
+            bw[lane] = c.w;
+            if (DZ == 1) {                                         // exclusive prefix sums of the chunk's weights: bw[32 + j] = w_0 + .. + w_{j-1}
+                double ps = c.w;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, ps, o); if (lane >= o) ps += t; }
+                bw[33 + lane] = ps;
+                if (lane == 0) bw[32] = 0.0;
+            }
+        }
+        __syncwarp();
     };
 
     unsigned long long nvis2 = 0;
-    {
+    if constexpr (RANKED) {
+        RChunk nxt = load_rchunk(cmin), cur;
+        for (int c = cmin; c <= cmax; c++) {
+            cur = nxt;
+            if (c < cmax) nxt = load_rchunk(c + 1);
+            stage_r(cur);
+            bool all = Q == 1;
+            #pragma unroll
+            for (int q = 0; q < Q - 1; q++) all |= (c >= clo[q]) & (c <= chi[q]);
+            if (all) count_body_rank(std::integral_constant<int, 0>{}, c * 32);
+            else     count_body_rank(std::integral_constant<int, Q - 1>{}, c * 32);
+            nvis2 += all ? Q : 1;
+        }
+    } else {
         Chunk<D, WEIGHTED> nxt = load_chunk<D, WEIGHTED>(jd, cmin, lane, n), cur;
         for (int c = cmin; c <= cmax; c++) {
             cur = nxt;

@@ -29,7 +29,7 @@ class FakeHandle:
                 x, y, z = o.lagged_columns(expr[jb["src"]], expr[jb["dst"]], int(jb["delay"]), differential)
             else:
                 x, y, z = o.crdi_columns(expr, int(jb["src"]), int(jb["dst"]), int(jb["delay"]),
-                                         [int(v) for v in jb["cond_gene"][:L]], [int(v) for v in jb["cond_delay"][:L]])
+                                         [int(v) for v in jb["cond_gene"][:L]], [int(v) for v in jb["cond_delay"][:L]], differential)
             if scales is not None:
                 x, y, z = x / scales[j, 0], y / scales[j, 1], z / scales[j, 2]
             out[j] = est(x, y, z)
@@ -50,3 +50,42 @@ class FakeHandle:
                 x, y, z = x[keep], y[keep], z[keep]
             out[j] = o.cmi(x, y, z)
         return out
+
+    # ---- consumers of the causal matrix: numpy restatements of Scribe.py:142-176, plot/networks.py:34-47, causal_network.py:337-389
+    def clr(self, M, both_dims):
+        mat = np.asarray(M, dtype=float)
+        sq = mat.shape[0] == mat.shape[1]
+
+        def z(axis):
+            v = np.round(mat, 10)
+            mu, sd = np.mean(mat, axis=axis), np.std(mat, axis=axis, ddof=1)
+            if not sq:
+                mu = mu[:, None] if axis == 1 else mu[None, :]
+                sd = sd[:, None] if axis == 1 else sd[None, :]
+            v = (v - mu) / sd
+            v[v < 0] = 0
+            return v
+
+        zr = z(1)
+        return np.sqrt((zr ** 2 + z(0) ** 2) / 2) if both_dims else np.sqrt(zr ** 2)
+
+    def top_edges(self, M, n_top):
+        M = np.asarray(M, dtype=float).copy()
+        M[(M - M.T) < 0] = np.nan
+        i, j = np.nonzero(~np.isnan(M))
+        order = np.argsort(-M[i, j], kind="stable")[:n_top]
+        return i[order].astype(np.int32), j[order].astype(np.int32), M[i, j][order]
+
+    def roc(self, scores, truth):
+        n = scores.shape[0]
+        i, j = np.nonzero(~np.eye(n, dtype=bool))
+        order = np.argsort(-scores[i, j], kind="stable")
+        hit = truth[i, j][order].astype(bool)
+        tp = np.concatenate(([0], np.cumsum(hit))); fp = np.concatenate(([0], np.cumsum(~hit)))
+        if tp[-1] == 0 or fp[-1] == 0:
+            raise ZeroDivisionError("float division by zero")
+        x = fp / float(fp[-1]); y = tp / float(tp[-1])
+        a = 0
+        for t in range(1, len(x)):
+            a += abs((x[t] - x[t - 1]) * (y[t] + y[t - 1]) / 2)
+        return a, x, y

@@ -13,6 +13,7 @@ Writes tests/golden/golden_configs.npz (merged with what is already there, so pa
   c4    multi-run-form rdi([1,5,10]) + crdi(L=2) on recipes.C4_GENES of the C4 panel (200 genes x 5000 cells): 126 + 42 values.
   c5    rdi([1,5,10], uniformization=True) (cumi, KDE bw = 0.01) on recipes.C5_GENES of the z-scored C5 panel
         (1000 genes x 20 000 cells): 36 values at N = 19 999 / 19 995 / 19 990.
+  diffcrdi  differential-mode rdi + crdi on GV-E (multi-run), L = 1, 2.
   post  CLR, roc, normalize, smooth, load_anndata, top-n edges: the reference's own post-/pre-processing functions on small inputs.
 
 Run in the build container only.  Loader as in make_golden.py (stub matplotlib, /tmp copy of causal_network.py whose only
@@ -187,7 +188,21 @@ def part_post(procs):
     return out
 
 
-PARTS = {"c2": part_c2, "c3": part_c3, "c4": part_c4, "c5": part_c5, "post": part_post}
+def part_diffcrdi(procs):
+    """differential-mode rdi + crdi (multi-run branch, causal_network.py:257-283 with :271): GV-E, L = 1 and 2"""
+    _, cn, _, _ = ref()
+    runs, g6, delays = recipes.gv_e()
+    df = recipes.multi_run_frame(runs, g6)
+    m = cn.causal_model(); m.expression = df; m.expression_raw = df
+    m.node_ids = df.index.levels[0]; m.run_ids = df.index.levels[1]
+    r = m.rdi(delays, differential_mode=True)
+    out = {"e_rdi_diff_%d" % d: r[d].to_numpy(dtype=float) for d in delays}
+    out["e_crdi_diff_L1"] = m.crdi(L=1, differential_mode=True).to_numpy(dtype=float)
+    out["e_crdi_diff_L2"] = m.crdi(L=2, differential_mode=True).to_numpy(dtype=float)
+    return out
+
+
+PARTS = {"diffcrdi": part_diffcrdi, "c2": part_c2, "c3": part_c3, "c4": part_c4, "c5": part_c5, "post": part_post}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -393,6 +393,11 @@ def test_windowed_sweep_extreme_scales(S, dz, scale):
     b = S.information_estimators.ksg_debug("cmi", x, y, z, path="sweep")
     assert np.array_equal(a["eps"], b["eps"]) and np.array_equal(a["counts"], b["counts"])
     assert np.isfinite(a["eps"]).all() and (a["counts"][0] >= 5).all()
+    # and the dense kernel itself against the oracle at this scale (the comparison above is otherwise self-referential)
+    P = np.concatenate((x, y, z), axis=1)
+    iz = tuple(range(2, 2 + dz))
+    eps, cnt = o.knn_counts(P, [(0, 1) + iz, (0,) + iz, (1,) + iz, iz], 5)
+    assert np.array_equal(a["eps"], eps) and np.array_equal(a["counts"], cnt)
 
 
 @pytest.mark.gpu
@@ -526,3 +531,154 @@ def test_mi_sweep_ragged_sizes(S):
         assert np.array_equal(np.asarray(a["counts"])[:3], np.asarray(b["counts"])[:3]), n
         eps, cnt = o.knn_counts(np.concatenate((x, y), axis=1), [(0, 1), (0,), (1,)], 5)
         assert np.array_equal(b["eps"], eps) and np.array_equal(np.asarray(b["counts"])[:3], cnt), n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config-scale parity: the named BASELINE configs at their full sizes against outputs of the UNMODIFIED reference
+# (tests/golden/make_golden_configs.py -> golden_configs.npz)
+# ---------------------------------------------------------------------------------------------------------------
+def _top_edges(M, n):
+    """the n strongest ordered pairs of a score matrix (diagonal excluded), strongest first; ties broken by (source, target)"""
+    G = M.shape[0]
+    a, b = np.nonzero(~np.eye(G, dtype=bool))
+    order = np.lexsort((b, a, -M[a, b]))
+    return list(zip(a[order[:n]].tolist(), b[order[:n]].tolist()))
+
+
+def test_config_c2_full_matrix(S, golden_configs):
+    """BASELINE configs[1] in full: all 29 700 values of rdi([1,5,10]) on 100 genes x 2000 cells, and the top-100 edge ranking
+    of the MAX matrix (9 900 edges)"""
+    E = recipes.rdi_synthetic(100, 2000, 2)
+    m = S.causal_model(pd.DataFrame(E, index=pd.Index(["g%03d" % i for i in range(100)], name="GENE_ID")))
+    r = m.rdi([1, 5, 10])
+    ref_max = np.full((100, 100), -np.inf)
+    for d in (1, 5, 10):
+        got, ref = r[d].to_numpy(dtype=float), golden_configs["c2full_rdi_%d" % d]
+        assert np.isnan(np.diag(got)).all()
+        assert np.nanmax(np.abs(got - ref)) <= TOL_EXACT, d
+        ref_max = np.fmax(ref_max, ref)
+    got_max = r["MAX"].to_numpy(dtype=float)
+    off = ~np.eye(100, dtype=bool)
+    assert np.abs(got_max[off] - ref_max[off]).max() <= TOL_EXACT
+    assert _top_edges(got_max, 100) == _top_edges(ref_max, 100)
+
+
+def test_config_c3_sampled_pairs(S, golden_configs):
+    """BASELINE configs[2]: 38 (TF, target) pairs of the 500 genes x 10 000 cells dynamics-coupling panel through the public
+    driver (device normalisation of the full-width layers included)"""
+    spl, vel, genes = recipes.coupling_panel(500, 10000, 3)
+    ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
+    tfs = [genes[i] for i in recipes.C3_TFS]; tg = [genes[i] for i in recipes.C3_TARGETS]
+    S.causal_net_dynamics_coupling(ad, TFs=tfs, Targets=tg)
+    got = ad.uns["causal_net"]["RDI"].loc[tfs, tg].to_numpy(dtype=float)
+    assert np.abs(got - golden_configs["c3_matrix"]).max() <= TOL_EXACT
+    assert (got[[1, 3], [1, 4]] == 0).all()                     # g0077 / g0251 are TF and target: skipped pairs read 0
+
+
+def test_config_c4_rdi_crdi(S, golden_configs):
+    """BASELINE configs[3]: multi-run-form rdi([1,5,10]) + crdi(L=2) (D = 5) on 7 genes x 5000 cells of the C4 panel"""
+    E = recipes.ar_panel(200, 5000, 4)[recipes.C4_GENES]
+    names = ["g%04d" % i for i in recipes.C4_GENES]
+    m = S.causal_model(recipes.multi_run_frame([E], names))
+    r = m.rdi([1, 5, 10])
+    for d in (1, 5, 10):
+        assert np.nanmax(np.abs(r[d].loc[names, names].to_numpy(dtype=float) - golden_configs["c4_rdi_%d" % d])) <= TOL_EXACT
+    assert np.array_equal(np.isneginf(r["MAX"].to_numpy(dtype=float)), np.isneginf(golden_configs["c4_rdi_MAX"]))
+    c = m.crdi(L=2).loc[names, names].to_numpy(dtype=float)
+    assert np.nanmax(np.abs(c - golden_configs["c4_crdi_L2"])) <= TOL_EXACT
+
+
+def test_config_c5_uniformised(S, golden_configs):
+    """BASELINE configs[4]: 36 uniformised-RDI (cumi, KDE bw = 0.01) values at N = 19 999 / 19 995 / 19 990"""
+    E = recipes.zscore_rows(recipes.ar_panel(1000, 20000, 5))[recipes.C5_GENES]
+    m = S.causal_model(pd.DataFrame(E, index=pd.Index(["g%d" % i for i in range(len(E))], name="GENE_ID")))
+    r = m.rdi([1, 5, 10], uniformization=True)
+    for d in (1, 5, 10):
+        assert np.nanmax(np.abs(r[d].to_numpy(dtype=float) - golden_configs["c5_urdi_%d" % d])) <= TOL_KDE, d
+
+
+def test_crdi_differential_mode_gpu(S, golden_configs):
+    """differential-mode rdi + crdi (multi-run branch of the reference, causal_network.py:257-283 with :271)"""
+    runs, genes, delays = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    r = m.rdi(delays, differential_mode=True)
+    for d in delays:
+        assert np.allclose(r[d].to_numpy(dtype=float), golden_configs["e_rdi_diff_%d" % d], atol=TOL_EXACT, rtol=0, equal_nan=True)
+    for L in (1, 2):
+        c = m.crdi(L=L, differential_mode=True).to_numpy(dtype=float)
+        assert np.allclose(c, golden_configs["e_crdi_diff_L%d" % L], atol=TOL_EXACT, rtol=0, equal_nan=True), L
+
+
+def test_device_layer_normalisation_bit_identical(S):
+    """scribe_upload_coupling_raw: the device-normalised S / Y rows are the same float64 as the reference's pandas expressions
+    (Scribe.py:101-106,:121) for every gene; a NaN in the t0 layer is reported so the driver takes the host path"""
+    from scribe_py_b200 import Scribe as SC
+    rng = np.random.default_rng(5)
+    for n_cells, n_genes in ((500, 20), (1037, 7), (130, 3), (10000, 12)):
+        spl = rng.gamma(2., 1., (n_cells, n_genes)); spl[rng.random((n_cells, n_genes)) < 0.2] = 0
+        vel = 0.1 * rng.standard_normal((n_cells, n_genes)); vel[rng.random((n_cells, n_genes)) < 0.01] = np.nan
+        genes = ["g%02d" % i for i in range(n_genes)]
+        ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
+        h = S._lib.default_handle()
+        for normalize, t1 in ((True, "velocity"), (False, "velocity"), (True, "other")):
+            ad.layers["other"] = np.abs(vel)
+            Sp, Yp, _ = SC._normalised_layers_pandas(ad, genes, "spliced", t1, normalize)
+            assert h.upload_coupling_raw(spl, ad.layers[t1], normalize, t1 == "velocity")
+            for g in range(n_genes):
+                assert np.array_equal(h.read_coupling_row(0, g, n_cells), Sp[g], equal_nan=True)
+                assert np.array_equal(h.read_coupling_row(1, g, n_cells), Yp[g], equal_nan=True)
+    bad = spl.copy(); bad[3, 1] = np.nan
+    assert not h.upload_coupling_raw(bad, np.nan_to_num(vel), True, True)
+
+
+def test_post_processing_on_device(S, golden_configs, tmp_path):
+    """CLR (incl. the square-matrix broadcast quirk), roc and top-n edge extraction on the GPU against outputs of the reference's
+    own functions (Scribe.py:142-176, causal_network.py:337-389, plot/networks.py:34-47)"""
+    g = golden_configs
+    assert np.allclose(S.CLR(pd.DataFrame(g["clr_in_sq"])).to_numpy(), g["clr_sq"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_sq"], zscore_both_dim=False), g["clr_sq_rowonly"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_sym"]), g["clr_sym"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_rect"]), g["clr_rect"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_rect"], zscore_both_dim=True), g["clr_rect_both"], atol=1e-12, rtol=0)
+    names = ["Gene%d" % i for i in range(10)]
+    path = tmp_path / "true.txt"
+    path.write_text("".join("%s\t%s\n" % (names[a].upper() if a % 2 else names[a], names[b]) for a, b in g["roc_true"]))
+    m = S.causal_model(pd.DataFrame(np.zeros((10, 5)), index=pd.Index(names, name="GENE_ID")))
+    auroc, x, y = m.roc(pd.DataFrame(g["roc_scores"], index=names, columns=names), str(path))
+    assert auroc == pytest.approx(float(g["roc_auroc"]), abs=1e-15)
+    assert np.array_equal(x, g["roc_x"]) and np.array_equal(y, g["roc_y"])
+    with pytest.raises(ZeroDivisionError):
+        (tmp_path / "none.txt").write_text("nobody\tnothing\n")
+        m.roc(pd.DataFrame(g["roc_scores"], index=names, columns=names), str(tmp_path / "none.txt"))
+    n8 = ["n%d" % i for i in range(8)]
+    top = S.top_n_edges(pd.DataFrame(g["edges_in"], index=n8, columns=n8), top_n_edges=10)
+    assert np.array_equal(top["weight"].to_numpy(), g["edges_w"])
+    got = sorted(zip(top["weight"], top["source"], top["target"]))
+    ref = sorted(zip(g["edges_w"], [n8[i] for i in g["edges_src"]], [n8[i] for i in g["edges_dst"]]))
+    assert got == ref
+    # a larger matrix against the numpy restatement of the same three functions (tests/fake_device.py)
+    from fake_device import FakeHandle
+    rng = np.random.default_rng(3)
+    M = np.round(rng.gamma(1.5, 0.1, (300, 300)), 3); np.fill_diagonal(M, 0.0)        # rounded: plenty of ties
+    h, f = S._lib.default_handle(), FakeHandle()
+    assert np.allclose(h.clr(M, True), f.clr(M, True), atol=1e-12, rtol=0, equal_nan=True)
+    a, b, w = h.top_edges(M, 100); fa, fb, fw = f.top_edges(M, 100)
+    assert np.array_equal(a, fa) and np.array_equal(b, fb) and np.array_equal(w, fw)
+    truth = (rng.random((300, 300)) < 0.02).astype(np.uint8)
+    ga, gx, gy = h.roc(M, truth); ra, rx, ry = f.roc(M, truth)
+    assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and ga == pytest.approx(ra, abs=1e-15)
+
+
+def test_multi_gpu_invariance_torchrun():
+    """sharded == unsharded, bit for bit, on every GPU count this box offers (tools/check_multi_gpu.py under torchrun)"""
+    import os, subprocess, sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for world in sorted({2, n}):
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                            "--master-addr", "127.0.0.1", "--master-port", str(29610 + world),
+                            os.path.join(root, "tools", "check_multi_gpu.py")], capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0 and "OK bit-identical" in p.stdout, (p.stdout[-2000:], p.stderr[-2000:])

@@ -81,6 +81,30 @@ def test_clr_matches_definition(S):
     assert list(out.index) == list("abcde")
 
 
+def test_post_processing_against_reference(S, golden_configs, tmp_path):
+    """CLR / roc / top-n edges: the shims' argument handling and the formulas (here through the test double) against outputs
+    of the reference's own functions"""
+    g = golden_configs
+    assert np.allclose(S.CLR(pd.DataFrame(g["clr_in_sq"])).to_numpy(), g["clr_sq"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_sq"], zscore_both_dim=False), g["clr_sq_rowonly"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_sym"]), g["clr_sym"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_rect"]), g["clr_rect"], atol=1e-12, rtol=0)
+    assert np.allclose(S.CLR(g["clr_in_rect"], zscore_both_dim=True), g["clr_rect_both"], atol=1e-12, rtol=0)
+    names = ["Gene%d" % i for i in range(10)]
+    path = tmp_path / "true.txt"
+    path.write_text("".join("%s\t%s\n" % (names[a].upper() if a % 2 else names[a], names[b]) for a, b in g["roc_true"]))
+    m = S.causal_model(pd.DataFrame(np.zeros((10, 5)), index=pd.Index(names, name="GENE_ID")))
+    auroc, x, y = m.roc(pd.DataFrame(g["roc_scores"], index=names, columns=names), str(path))
+    assert auroc == pytest.approx(float(g["roc_auroc"]), abs=1e-12)
+    assert np.allclose(x, g["roc_x"], atol=1e-15, rtol=0) and np.allclose(y, g["roc_y"], atol=1e-15, rtol=0)
+    n8 = ["n%d" % i for i in range(8)]
+    top = S.top_n_edges(pd.DataFrame(g["edges_in"], index=n8, columns=n8), top_n_edges=10)
+    assert np.array_equal(top["weight"].to_numpy(), g["edges_w"])
+    got = sorted(zip(top["weight"], top["source"], top["target"]))
+    ref = sorted(zip(g["edges_w"], [n8[i] for i in g["edges_src"]], [n8[i] for i in g["edges_dst"]]))
+    assert got == ref                                     # equal weights (the reciprocal tie) may come in either order
+
+
 def test_slab_partition():
     from scribe_py_b200.distributed import slab
     for n in (0, 1, 7, 8, 29700, 249500):
@@ -90,6 +114,23 @@ def test_slab_partition():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_crdi_differential_mode(S, golden_configs):
+    """differential-mode rdi + crdi against the unmodified reference (multi-run branch; per-job np.std scales computed on the host)"""
+    from oracle import ksg_oracle as o
+    runs, genes, delays = recipes.gv_e()
+    m = S.causal_model(recipes.multi_run_frame(runs, genes))
+    r = m.rdi(delays, differential_mode=True)
+    for d in delays:
+        assert np.allclose(r[d].to_numpy(dtype=float), golden_configs["e_rdi_diff_%d" % d], atol=1e-12, rtol=0, equal_nan=True)
+    for L in (1, 2):
+        c = m.crdi(L=L, differential_mode=True).to_numpy(dtype=float)
+        assert np.allclose(c, golden_configs["e_crdi_diff_L%d" % L], atol=1e-12, rtol=0, equal_nan=True), L
+    # and the oracle's own differential cRDI against the same fixture
+    er = [[rr[g] for rr in runs] for g in range(len(genes))]
+    res = {d: golden_configs["e_rdi_diff_%d" % d] for d in delays}
+    assert np.allclose(o.crdi(er, res, delays, L=2, differential_mode=True), golden_configs["e_crdi_diff_L2"], atol=1e-12, rtol=0, equal_nan=True)
 
 
 def _gloo_worker(rank, world, port, q):
@@ -106,6 +147,21 @@ def _gloo_worker(rank, world, port, q):
 
     out = sharded_evaluate(101, evaluate)
     ok = bool(np.array_equal(out, np.arange(101, dtype=np.float64) ** 2 + 0.5)) and len(seen) == 1
+    # a rank that fails must not leave the others waiting in the all-gather: every rank raises
+    from scribe_py_b200.distributed import ShardError
+
+    def failing(lo, hi):
+        if rank == 1:
+            raise ValueError("delay leaves no samples")
+        return np.zeros(hi - lo)
+
+    try:
+        sharded_evaluate(40, failing)
+        ok = False
+    except ValueError:
+        ok = ok and rank == 1
+    except ShardError as e:
+        ok = ok and rank == 0 and "[1]" in str(e)
     # the full rdi() driver, sharded: every rank must end up with the complete matrices
     fake = FakeHandle()
     s._lib.default_handle = lambda device=None: fake

@@ -31,7 +31,18 @@ S.causal_net_dynamics_coupling(ad1)
 cp1 = ad1.uns["causal_net"]["RDI"].to_numpy(dtype=float)
 u1 = m1.rdi([1], uniformization=True)[1].to_numpy(dtype=float)
 D.world = real_world
-ok = all(np.array_equal(r[d].to_numpy(), r1[d].to_numpy(), equal_nan=True) for d in (1, 5, "MAX")) and \
+# a failing rank raises everywhere instead of hanging the others in the all-gather
+def failing(lo, hi, out_dev_ptr=None):
+    if dist.get_rank() == 1:
+        raise ValueError("delay leaves no samples")
+    return None if out_dev_ptr is not None else np.zeros(hi - lo)
+try:
+    D.sharded_evaluate(64, failing, S._lib.default_handle()); raised = False
+except ValueError:
+    raised = dist.get_rank() == 1
+except D.ShardError:
+    raised = dist.get_rank() != 1
+ok = raised and all(np.array_equal(r[d].to_numpy(), r1[d].to_numpy(), equal_nan=True) for d in (1, 5, "MAX")) and \
     np.array_equal(c.to_numpy(), c1.to_numpy(), equal_nan=True) and np.array_equal(cp, cp1) and np.array_equal(u, u1, equal_nan=True)
 t = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if dist.get_rank() == 0:

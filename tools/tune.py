@@ -52,9 +52,63 @@ def run_mi(G, T, reps=2):
              float(np.nansum(v))), flush=True)
 
 
+def run_panel(name, E, delays, est, reps=2):
+    """all ordered pairs x delays of an expression panel through scribe_lagged_jobs"""
+    G = E.shape[0]
+    h = _lib.default_handle()
+    h.upload_matrix(E)
+    src, dst = np.nonzero(~np.eye(G, dtype=bool))
+    jobs = np.zeros(len(src) * len(delays), dtype=_lib.JOB_DTYPE)
+    for i, d in enumerate(delays):
+        sl = slice(i * len(src), (i + 1) * len(src))
+        jobs["src"][sl] = src; jobs["dst"][sl] = dst; jobs["delay"][sl] = d
+    opts = _lib.make_opts(est, 5)
+    best = None
+    for _ in range(reps + 1):
+        v = h.lagged_jobs(jobs, opts)
+        st = h.stats()
+        if best is None or st["estimator_ms"] < best["estimator_ms"]:
+            best = st
+    print("AB %-12s jobs=%d est_ms=%.3f total_ms=%.3f visited=%.4f checksum=%.12f"
+          % (name, len(jobs), best["estimator_ms"], best["total_ms"],
+             (best["visited_knn"] + best["visited_count"]) / max(2.0 * best["point_pairs"], 1), float(np.nansum(v))), flush=True)
+
+
+def run_coupling(name, G, N, reps=2):
+    """dynamics coupling (C3 generator), all ordered pairs of the first G genes"""
+    spl, vel, genes = recipes.coupling_panel(G, N, 3)
+    s = (spl - spl.mean(0)) / (spl.max(0) - spl.min(0)); v = (vel - vel.mean(0)) / (vel.max(0) - vel.min(0))
+    h = _lib.default_handle()
+    h.upload_coupling(np.ascontiguousarray(s.T), np.ascontiguousarray((s + v).T))
+    src, dst = np.nonzero(~np.eye(G, dtype=bool))
+    opts = _lib.make_opts(_lib.EST_CMI, 5)
+    best = None
+    for _ in range(reps + 1):
+        out = h.coupling_jobs(src.astype(np.int32), dst.astype(np.int32), opts, True)
+        st = h.stats()
+        if best is None or st["estimator_ms"] < best["estimator_ms"]:
+            best = st
+    print("AB %-12s jobs=%d est_ms=%.3f total_ms=%.3f visited=%.4f checksum=%.12f"
+          % (name, len(src), best["estimator_ms"], best["total_ms"],
+             (best["visited_knn"] + best["visited_count"]) / max(2.0 * best["point_pairs"], 1), float(np.nansum(out))), flush=True)
+
+
+def run_ab():
+    """the three workloads the kernel variants are compared on (tools/ab.py)"""
+    run_panel("c2", recipes.rdi_synthetic(100, 2000, 2), [1, 5, 10], _lib.EST_CMI)
+    run_coupling("c3sub", 80, 10000)
+    E5 = recipes.zscore_rows(recipes.ar_panel(1000, 20000, 5)[:16])
+    run_panel("c5slab_cumi", E5, [1], _lib.EST_CUMI, reps=1)
+    run_panel("c5slab_cmi", E5, [1], _lib.EST_CMI, reps=1)
+    E4 = recipes.ar_panel(200, 5000, 4)[:40]
+    run_panel("c4sub", E4, [1, 5, 10], _lib.EST_CMI, reps=1)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "cmi"
-    if what == "cmi":
+    if what == "ab":
+        run_ab()
+    elif what == "cmi":
         run(60, 2000, [1, 5, 10], _lib.EST_CMI)
         run(24, 20000, [1], _lib.EST_CMI)
     elif what == "cumi":
