@@ -129,6 +129,16 @@ int scribe_debug_counts(scribe_handle* h, const double* x, const double* y, cons
  * at causal_network.py:140-176 / :223-283.  The matrix stays resident until the next upload. */
 int scribe_upload_matrix(scribe_handle* h, const double* E, int64_t n_genes, int64_t n_cells,
                          const int64_t* run_offsets, int32_t n_runs);
+/* causal_model.normalize (causal_network.py:104-109) in place on the resident matrix: every (gene, run) row -> (v - mean) /
+ * std(ddof = 1), NaN -> 0.  mean_order / avg_order select the summation order (0 numpy pairwise, 1 sequential) of the row sum
+ * behind the mean and of the one inside the variance, so that the caller can reproduce its pandas build bit for bit. */
+int scribe_normalize_resident(scribe_handle* h, int32_t mean_order, int32_t avg_order);
+/* causal_model.smooth (causal_network.py:97-101): the resident matrix is replaced by its rolling mean over `window` cells
+ * along every (gene, run) row (pandas' Kahan-compensated online mean); every run shrinks by window - 1 cells.
+ * new_n_cells / new_run_offsets (n_runs + 1 entries; either may be NULL) receive the new layout. */
+int scribe_smooth_resident(scribe_handle* h, int32_t window, int64_t* new_n_cells, int64_t* new_run_offsets);
+/* Rows [gene0, gene0 + n_genes) of the resident matrix back to the host (n_genes x n_cells doubles). */
+int scribe_read_matrix(scribe_handle* h, int64_t gene0, int64_t n_genes, double* out);
 /* Evaluate jobs against the resident matrix.  opts->estimator is CMI (uniformization=False) or CUMI.
  * differential != 0: y = e_dst[p-1] - e_dst[p] (causal_network.py:153,:173).
  * scales: NULL, or 3 doubles per job {sx, sy, sz}; each role is divided by its scale (the caller computes
@@ -181,6 +191,12 @@ int scribe_top_edges(scribe_handle* h, const double* M, int64_t n, int64_t n_top
  * (may be NULL) receive n*(n-1)+1 points when no score is NaN.  SCRIBE_E_DOMAIN when there is no true or no false edge
  * (the reference divides by zero there). */
 int scribe_roc(scribe_handle* h, const double* scores, const uint8_t* truth, int64_t n, double* auroc, double* fpr, double* tpr);
+
+/* kNN grid regressor of viz_causality / viz_comb_logic (Scribe/plot/heatmaps.py:405-423, :578-596): for each of the m query
+ * points (qx, qy) the k+1 Euclidean-nearest of the n data points (px, py) -- tree.query(q, k + 1) -- the nearest dropped,
+ * weights exp(-d / min d) normalised to 1, out[q] = sum w * value[neighbour].  1 <= k <= 15. */
+int scribe_knn_regress(scribe_handle* h, const double* px, const double* py, const double* value, int64_t n,
+                       const double* qx, const double* qy, int64_t m, int32_t k, double* out);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ Module layout mirrors the reference package for the path it replaces (Scribe/__i
     other_estimators       : mi, corr (pairwise networks over a causal_model)
     read_export            : load_anndata (AnnData -> causal_model, branches as runs ordered by pseudotime)
     networks               : top_n_edges (the edge table behind plot.networks.vis_causal_net)
+    heatmaps               : causality_grid, comb_logic_grid (the kNN grid regressors behind plot.heatmaps)
 All estimator arithmetic runs in libscribe_b200.so (CUDA, FP64); there is no CPU fallback.
 """
 from . import _lib
@@ -16,6 +17,7 @@ from . import Scribe
 from . import read_export
 from . import other_estimators
 from . import networks
+from . import heatmaps
 from .information_estimators import vd, mi, cmi, umi, cumi
 from .causal_network import causal_model
 from .Scribe import causal_net_dynamics_coupling, CLR
@@ -23,5 +25,5 @@ from .read_export import load_anndata
 from .networks import top_n_edges
 
 __all__ = ["information_estimators", "causal_network", "Scribe", "vd", "mi", "cmi", "umi", "cumi", "causal_model",
-           "causal_net_dynamics_coupling", "CLR", "load_anndata", "read_export", "other_estimators", "networks", "top_n_edges"]
+           "causal_net_dynamics_coupling", "CLR", "load_anndata", "read_export", "other_estimators", "networks", "top_n_edges", "heatmaps"]
 __version__ = "0.1.0"

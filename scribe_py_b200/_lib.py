@@ -49,9 +49,9 @@ _lib_lock = threading.Lock()
 # every symbol include/scribe_b200.h declares
 EXPORTS = [
     "scribe_abi_version", "scribe_last_error", "scribe_create", "scribe_destroy", "scribe_device_info",
-    "scribe_get_stats", "scribe_device_index", "scribe_estimate", "scribe_debug_counts", "scribe_upload_matrix", "scribe_lagged_jobs",
+    "scribe_get_stats", "scribe_device_index", "scribe_estimate", "scribe_debug_counts", "scribe_upload_matrix", "scribe_normalize_resident", "scribe_smooth_resident", "scribe_read_matrix", "scribe_lagged_jobs",
     "scribe_lagged_jobs_dev", "scribe_mi_jobs", "scribe_upload_coupling", "scribe_upload_coupling_raw", "scribe_read_coupling_row", "scribe_coupling_jobs", "scribe_coupling_jobs_dev",
-    "scribe_clr", "scribe_top_edges", "scribe_roc",
+    "scribe_clr", "scribe_top_edges", "scribe_roc", "scribe_knn_regress",
 ]
 
 
@@ -77,6 +77,9 @@ def load_library():
         lib.scribe_estimate.argtypes = [P, P, P, P, I64, I32, I32, I32, C.POINTER(Opts), D]
         lib.scribe_debug_counts.argtypes = [P, P, P, P, I64, I32, I32, I32, C.POINTER(Opts), P, P, P, P]
         lib.scribe_upload_matrix.argtypes = [P, P, I64, I64, P, I32]
+        lib.scribe_normalize_resident.argtypes = [P, I32, I32]
+        lib.scribe_smooth_resident.argtypes = [P, I32, C.POINTER(I64), P]
+        lib.scribe_read_matrix.argtypes = [P, I64, I64, P]
         lib.scribe_lagged_jobs.argtypes = [P, P, I64, C.POINTER(Opts), I32, P, P]
         lib.scribe_lagged_jobs_dev.argtypes = [P, P, I64, C.POINTER(Opts), I32, P, P]
         lib.scribe_mi_jobs.argtypes = [P, P, P, I64, C.POINTER(Opts), P]
@@ -88,6 +91,7 @@ def load_library():
         lib.scribe_clr.argtypes = [P, P, I64, I64, I32, P]
         lib.scribe_top_edges.argtypes = [P, P, I64, I64, P, P, P, C.POINTER(I64)]
         lib.scribe_roc.argtypes = [P, P, P, I64, D, P, P]
+        lib.scribe_knn_regress.argtypes = [P, P, P, P, I64, P, P, I64, I32, P]
         _lib = lib
         return lib
 
@@ -144,6 +148,8 @@ class Handle:
         self.sm_count, self.clock_khz, self.mem_bytes = sm.value, clk.value, mem.value
         self.device_name = name.value.decode()
         self.device = int(self._lib.scribe_device_index(h))          # CUDA ordinal: collectives must run on the same GPU
+        self.resident_token = 0                                      # bumped whenever the resident expression matrix changes owner
+        self.resident_shape = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -202,6 +208,32 @@ class Handle:
                                             0 if ro is None else len(ro) - 1)
         if rc != SCRIBE_OK:
             _raise(rc)
+        self.resident_token += 1
+        self.resident_shape = E.shape
+        return self.resident_token
+
+    def normalize_resident(self, mean_order, avg_order):
+        rc = self._lib.scribe_normalize_resident(self._h, int(mean_order), int(avg_order))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+
+    def smooth_resident(self, window, n_runs):
+        n = C.c_int64(0)
+        off = np.zeros(n_runs + 1, dtype=np.int64)
+        rc = self._lib.scribe_smooth_resident(self._h, int(window), C.byref(n), _ptr(off))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        self.resident_shape = (self.resident_shape[0], int(n.value))
+        return off
+
+    def read_matrix(self, gene0=0, n_genes=None):
+        G, N = self.resident_shape
+        n_genes = G - gene0 if n_genes is None else n_genes
+        out = np.empty((n_genes, N))
+        rc = self._lib.scribe_read_matrix(self._h, int(gene0), int(n_genes), _ptr(out))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return out
 
     def lagged_jobs(self, jobs, opts, differential=False, scales=None, out_dev_ptr=None):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
@@ -309,6 +341,17 @@ class Handle:
         if rc != SCRIBE_OK:
             _raise(rc)
         return a.value, x, y
+
+
+    def knn_regress(self, px, py, value, qx, qy, k=5):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (px, py, value, qx, qy)]
+        assert len(a[0]) == len(a[1]) == len(a[2]) and len(a[3]) == len(a[4])
+        out = np.empty(len(a[3]))
+        rc = self._lib.scribe_knn_regress(self._h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), len(a[0]), _ptr(a[3]), _ptr(a[4]), len(a[3]),
+                                          int(k), _ptr(out))
+        if rc != SCRIBE_OK:
+            _raise(rc)
+        return out
 
 
 _default = {}

@@ -60,7 +60,36 @@ class causal_model(object):
     """Holds gene expression (genes x cells, single-run index GENE_ID or MultiIndex (GENE_ID, RUN_ID)) and
     computes pairwise RDI / cRDI scores on the GPU."""
 
+    # ------------------------------------------------------------------ expression: host frame <-> matrix resident on the GPU
+    # `expression` is the reference's public attribute (causal_network.py:15-23).  Here it is a property over two copies of the
+    # same data: the host DataFrame and the dense matrix resident on the device.  rdi()/crdi() upload the matrix once and reuse it
+    # while the frame is unchanged; normalize()/smooth() transform the resident matrix in place and the frame is rebuilt from the
+    # device only when somebody reads it.  Assigning a frame invalidates the device copy.  (Mutating the assigned frame in place
+    # is not seen: call invalidate_device() after doing that.)
+    @property
+    def expression(self):
+        if getattr(self, "_expr_stale", False):
+            self._materialise_expression()
+        try:
+            return self._expr
+        except AttributeError:
+            raise AttributeError("'causal_model' object has no attribute 'expression'") from None
+
+    @expression.setter
+    def expression(self, frame):
+        self._expr = frame
+        self._expr_stale = False
+        self._dev = None
+
+    def invalidate_device(self):
+        """Forget the matrix resident on the GPU (after an in-place edit of model.expression)."""
+        if getattr(self, "_expr_stale", False):
+            self._materialise_expression()
+        self._dev = None
+
     def __init__(self, expression=None):
+        self._dev = None
+        self._expr_stale = False
         if expression is None:
             warnings.warn(" WARNING: No expression data argument given. if you intend to load the data from a file, "
                           "call the method 'read_expression_file'.")
@@ -127,15 +156,185 @@ class causal_model(object):
             self.run_ids = subset
 
     def smooth(self, window):
-        """Rolling mean along the cell axis (causal_network.py:97-101; written without the removed axis= kwarg)."""
+        """Rolling mean of expression_raw along the cell axis, all-NaN columns dropped (causal_network.py:97-101; the reference's
+        axis= kwarg no longer exists in pandas, `.T.rolling(window).mean().T` is the same computation).  Runs on the GPU when
+        the raw matrix has no NaN padding and the device result reproduces pandas on probe rows; otherwise in pandas."""
+        if self._smooth_on_device(window):
+            return
         sm = self.expression_raw.T.rolling(window=window).mean().T
         self.expression = sm.dropna(axis=1, how="all")
 
     def normalize(self):
-        """z-score every row, NaN -> 0 (causal_network.py:104-109)."""
-        e = self.expression.sub(self.expression.mean(axis=1), axis=0)
-        e = e.div(self.expression.std(axis=1), axis=0)
+        """z-score every row, NaN -> 0 (causal_network.py:104-109).  Runs in place on the matrix resident on the GPU (uploading
+        it first if necessary) when that reproduces pandas bit for bit on probe rows; otherwise in pandas."""
+        if self._normalize_on_device():
+            return
+        cur = self.expression
+        e = cur.sub(cur.mean(axis=1), axis=0)
+        e = e.div(cur.std(axis=1), axis=0)
         self.expression = e.fillna(0)
+
+    # ------------------------------------------------------------------ device-side preprocessing
+    @staticmethod
+    def _ordered_sum(v, order):
+        if order == 0:
+            return float(np.add.reduce(np.ascontiguousarray(v)))      # numpy pairwise
+        s = 0.0
+        for x in v:
+            s += x
+        return s
+
+    def _probe_rows(self, n_rows):
+        return sorted(set([0, n_rows // 2, n_rows - 1]))
+
+    def _normalize_on_device(self):
+        h = _lib.default_handle()
+        if not hasattr(h, "normalize_resident"):
+            return False
+        try:
+            node_ids, run_off, _ = self._ensure_resident()
+        except AssertionError:
+            return False
+        lay = self._dev
+        if lay is None or lay["padded"]:
+            return False                                           # NaN padding: pandas sums the padded rows, not reproduced here
+        # which summation orders does this pandas use?  (3 probe rows, host; the stale frame is never needed: probe from the device)
+        n_runs = len(run_off) - 1
+        probe = self._probe_rows(len(node_ids))
+        rows = np.stack([h.read_matrix(g, 1)[0] for g in probe])
+        want = []
+        for r in range(n_runs):
+            # pandas on a frame of the probe rows (several rows on purpose: the summation order of DataFrame.mean(axis=1)
+            # depends on the frame's memory layout, and a one-row frame is laid out differently from a many-row one)
+            f = pd.DataFrame(rows[:, run_off[r]:run_off[r + 1]].copy())
+            z = f.sub(f.mean(axis=1), axis=0).div(f.std(axis=1), axis=0).fillna(0).to_numpy()
+            for i in range(len(probe)):
+                want.append((rows[i, run_off[r]:run_off[r + 1]], z[i]))
+        pick = None
+        for mo in (1, 0):
+            for ao in (0, 1):
+                ok = True
+                for seg, z in want:
+                    n = len(seg)
+                    mean = self._ordered_sum(seg, mo) / n
+                    avg = self._ordered_sum(seg, ao) / n
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        sd = np.sqrt(np.add.reduce((avg - seg) * (avg - seg)) / (n - 1))
+                        got = (seg - mean) / sd
+                    got[np.isnan(got)] = 0
+                    if not np.array_equal(got, z):
+                        ok = False
+                        break
+                if ok:
+                    pick = (mo, ao)
+                    break
+            if pick:
+                break
+        if pick is None:
+            return False
+        had_host_copy = not self._expr_stale
+        h.normalize_resident(*pick)
+        after = np.stack([h.read_matrix(g, 1)[0] for g in probe])      # the device must reproduce pandas on the probe rows
+        for r in range(n_runs):
+            for i in range(len(probe)):
+                if not np.array_equal(after[i, run_off[r]:run_off[r + 1]], want[r * len(probe) + i][1]):
+                    self._dev = None                               # the resident copy is no longer this model's frame
+                    if had_host_copy:
+                        return False                              # pandas redoes it on the host frame
+                    raise RuntimeError("device normalisation differs from pandas on a probe row and no host copy is left; "
+                                       "assign model.expression again")
+        self._expr_stale = True
+        return True
+
+    def _smooth_on_device(self, window):
+        h = _lib.default_handle()
+        if not hasattr(h, "smooth_resident"):
+            return False
+        raw = self.expression_raw
+        if not isinstance(raw, pd.DataFrame) or window < 1:
+            return False
+        keep_expr, keep_stale, keep_dev = getattr(self, "_expr", None), self._expr_stale, self._dev
+        try:
+            self._expr, self._expr_stale, self._dev = raw, False, None
+            node_ids, run_off, _ = self._ensure_resident()
+            lay = self._dev
+            if lay is None or lay["padded"] or min(np.diff(run_off)) < window:
+                raise AssertionError
+        except AssertionError:
+            self._expr, self._expr_stale, self._dev = keep_expr, keep_stale, keep_dev
+            return False
+        n_runs = len(run_off) - 1
+        probe = self._probe_rows(len(node_ids))
+        before = {g: h.read_matrix(g, 1)[0] for g in probe}
+        new_off = h.smooth_resident(window, n_runs)
+        for g in probe:
+            v = h.read_matrix(g, 1)[0]
+            for r in range(n_runs):
+                seg = before[g][run_off[r]:run_off[r + 1]]
+                want = pd.Series(seg).rolling(window=window).mean().to_numpy()[window - 1:]
+                if not np.array_equal(v[new_off[r]:new_off[r + 1]], want, equal_nan=True):
+                    self._expr, self._expr_stale, self._dev = keep_expr, keep_stale, None
+                    return False
+        lay = dict(lay)
+        lay["run_off"] = np.asarray(new_off, dtype=np.int64)
+        lay["columns"] = [c[window - 1:] for c in lay["columns"]]
+        lay["n_cells"] = int(new_off[-1])
+        self._dev = lay
+        self._expr_stale = True
+        return True
+
+    def _materialise_expression(self):
+        """Rebuild the host frame from the matrix resident on the device (after normalize()/smooth() ran there)."""
+        lay = self._dev
+        h = _lib.default_handle()
+        if lay is None or getattr(h, "resident_token", None) != lay["token"]:
+            raise RuntimeError("the device copy of model.expression was replaced before the frame was read back")
+        E = h.read_matrix()
+        ro = lay["run_off"]
+        if lay["runs"] == [None]:
+            frame = pd.DataFrame(E, index=lay["index"], columns=lay["columns"][0])
+        else:
+            width = max(len(c) for c in lay["columns"])
+            rows = np.full((len(lay["index"]), width), np.nan)
+            pos = {key: i for i, key in enumerate(lay["index"])}
+            for g_i, g in enumerate(lay["node_ids"]):
+                for r_i, run in enumerate(lay["runs"]):
+                    rows[pos[(g, run)], :ro[r_i + 1] - ro[r_i]] = E[g_i, ro[r_i]:ro[r_i + 1]]
+            frame = pd.DataFrame(rows, index=lay["index"])
+        self._expr = frame
+        self._expr_stale = False
+
+    @staticmethod
+    def _fingerprint(frame):
+        v = frame.to_numpy()
+        flat = v.reshape(-1) if v.flags["C_CONTIGUOUS"] else v.T.reshape(-1)
+        step = max(1, len(flat) // 4096)
+        return (id(frame), v.shape, hash(flat[::step].tobytes()))
+
+    def _ensure_resident(self):
+        """(node_ids, run_offsets, E or None): makes sure the dense matrix of the current expression is resident on this
+        rank's GPU.  E is None when the device already holds it (nothing was uploaded)."""
+        h = _lib.default_handle()
+        lay = self._dev
+        if lay is not None and getattr(h, "resident_token", None) == lay["token"] and \
+                (self._expr_stale or lay["fingerprint"] == self._fingerprint(self._expr)):
+            return lay["node_ids"], lay["run_off"], None
+        node_ids, E, run_off = self._dense()
+        token = h.upload_matrix(E, run_off)
+        expr = self._expr
+        runs = [None] if expr.index.nlevels == 1 else list(self.run_ids)
+        padded = bool(np.isnan(expr.to_numpy(dtype=np.float64)).any())
+        if runs == [None]:
+            columns = [list(expr.columns)]
+        else:
+            columns = [list(range(int(run_off[r + 1] - run_off[r]))) for r in range(len(runs))]
+        self._dev = None if token is None else {
+            "token": token, "fingerprint": self._fingerprint(expr), "node_ids": node_ids, "run_off": np.asarray(run_off, dtype=np.int64),
+            "runs": runs, "padded": padded, "index": expr.index if runs == [None] else list(expr.index), "columns": columns,
+            "n_cells": int(E.shape[1]), "E_host": None}
+        if runs == [None] and not (len(expr.index) == len(node_ids) and list(expr.index) == node_ids):
+            self._dev = None                                   # reordered / subset rows: no write-back layout, upload every time
+        return node_ids, run_off, E
 
     # ------------------------------------------------------------------ dense layout for the device
     def _dense(self):
@@ -240,7 +439,9 @@ class causal_model(object):
         """Host-side job table of one rdi() call: every ordered pair x delay, ordered delay-major, then
         target, then source, so that a rank's contiguous slab shares its targets' y/z columns."""
         delays = list(delays)
-        node_ids, E, run_off = self._dense()
+        node_ids, run_off, E = self._ensure_resident()              # uploads the matrix unless the device already holds it
+        if E is None and differential_mode:
+            E = _lib.default_handle().read_matrix()
         G = len(node_ids)
         tgt, src = np.meshgrid(np.arange(G, dtype=np.int32), np.arange(G, dtype=np.int32), indexing="ij")
         off = tgt != src
@@ -279,7 +480,6 @@ class causal_model(object):
         NaN diagonal)} plus "MAX", the element-wise maximum over delays (-inf diagonal).
         `number_of_processes` is accepted and ignored: parallelism comes from the GPU(s)."""
         plan = self._rdi_plan(delays, differential_mode)
-        _lib.default_handle().upload_matrix(plan["E"], plan["run_off"])
         vals = self._rdi_execute(plan, uniformization, differential_mode)
         delays, node_ids, src, tgt, per = plan["delays"], plan["node_ids"], plan["src"], plan["tgt"], plan["per"]
         G = len(node_ids)
@@ -301,7 +501,7 @@ class causal_model(object):
                      differential_mode=differential_mode)
         if L > _lib.MAX_COND:
             raise ValueError("crdi supports at most %d conditioning genes" % _lib.MAX_COND)
-        node_ids, E, run_off = self._dense()
+        node_ids, run_off, E = self._ensure_resident()
         G = len(node_ids)
         pos = {g: i for i, g in enumerate(node_ids)}
         max_val, max_delay = self.__extract_max_rdi_value_delay()
@@ -330,9 +530,10 @@ class causal_model(object):
                 keep_own = [s_ for s_ in range(L + 1) if s_ != s_own]
                 jobs["cond_gene"][row, :L] = slot_gene[keep_own]; jobs["cond_delay"][row, :L] = slot_delay[keep_own]
             j += G - 1
-        scales = self._crdi_scales(E, run_off, jobs, L) if differential_mode else None
         h = _lib.default_handle()
-        h.upload_matrix(E, run_off)
+        scales = None
+        if differential_mode:
+            scales = self._crdi_scales(h.read_matrix() if E is None else E, run_off, jobs, L)
         opts = _lib.make_opts(_lib.EST_CUMI if uniformization else _lib.EST_CMI, 5)
 
         def evaluate(lo, hi, out_dev_ptr=None):

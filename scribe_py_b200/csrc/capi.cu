@@ -62,6 +62,7 @@ struct scribe_handle {
     DevBuf keys_in, keys_out, vals_in, perm, sort_tmp, seg_off, keyspecs, visited, permS, strips, permE, sortedE, rawjobs;
     DevBuf post[8];                              // CLR / edge ranking / roc scratch
     DevBuf raw0, raw1, stat, nanflag;            // raw layers / row statistics of the on-device normalisation
+    DevBuf wcum;                                 // umi: prefix sums of the weights in sweep order
     DevBuf sorted, rankf, crank, sortedS, rankS, permY, sortedY, rankY, rankE;   // rank-space count pass: ascending values + float ranks
     bool sortE_valid = false;             // permE / sortedE describe the uploaded expression matrix
     scribe_stats st{};
@@ -170,7 +171,7 @@ SweepFn pick_sweepw_k(int kcap) {
 SweepFn pick_sweepw(int dx, int dy, int dz, int kcap, bool weighted) {
     if (dx != 1 || dy != 1) return nullptr;
     switch (dz) {
-        case 0: return weighted ? nullptr : pick_sweepw_k<0, false>(kcap);      // mi(x, y): sorted by y, x marginal by rank
+        case 0: return weighted ? pick_sweepw_k<0, true>(kcap) : pick_sweepw_k<0, false>(kcap);   // mi(x, y) / umi(x, y): sorted by y, marginals by rank
         case 1: return weighted ? pick_sweepw_k<1, true>(kcap) : pick_sweepw_k<1, false>(kcap);
         case 2: return weighted ? pick_sweepw_k<2, true>(kcap) : pick_sweepw_k<2, false>(kcap);
         case 3: return weighted ? pick_sweepw_k<3, true>(kcap) : pick_sweepw_k<3, false>(kcap);
@@ -221,6 +222,10 @@ bool want_sweep(const scribe_opts* o, int dx, int dy, int dz, int n_max) {
     const int kcap = (o->k + 1 <= 6) ? 6 : ((o->k + 1 <= 16) ? 16 : 0);
     if (o->estimator == SCRIBE_EST_MI) {                   // windowed sweep only (sorted by y; JobDesc.srt[0] for the x marginal)
         if (!kcap || !pick_sweepw(dx, dy, 0, kcap, false)) return false;
+        return o->path == SCRIBE_PATH_SWEEP || (o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N);
+    }
+    if (o->estimator == SCRIBE_EST_UMI) {                  // Euclidean variant of the windowed sweep (scalar x and y)
+        if (!kcap || !pick_sweepw(dx, dy, 0, kcap, true)) return false;
         return o->path == SCRIBE_PATH_SWEEP || (o->path == SCRIBE_PATH_AUTO && n_max >= SWEEP_MIN_N);
     }
     if (o->estimator != SCRIBE_EST_CMI && o->estimator != SCRIBE_EST_CUMI) return false;
@@ -305,7 +310,7 @@ struct DebugPtrs { double* eps = nullptr; int32_t* cnt = nullptr; double* wsum =
 // dbg (optional, single-chunk only): host pointers that receive the per-point quantities of job 0..n-1.
 void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int dy, int dz,
               const scribe_opts* o, double* out_dev, bool n_on_device, const DebugPtrs* dbg, bool* domain_error,
-              bool have_order = false, int64_t nj_dev = -1)
+              bool have_order = false, int64_t nj_dev = -1, bool* used_sweep = nullptr)
 {
     // nj_dev >= 0: the descriptors of nj_dev jobs (qoff included) were built in h->jobs on the device; `hj` is not used
     const bool host_desc = nj_dev < 0;
@@ -341,16 +346,17 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         const bool auto_strip = o->path == SCRIBE_PATH_AUTO && dz == 1 && weighted && h->sweep_v1;   // the windowed sweep beats both strip forms
         if (o->path == SCRIBE_PATH_STRIP || auto_strip) strip = pick_strip(dx, dy, dz, kcap, weighted);
         use_strip2 = dz == 1 && !h->no_strip2 && (o->path == SCRIBE_PATH_STRIP || n_max >= 4096);
-        sweep = pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
+        sweep = (dz == 0) ? nullptr : pick_sweep(dx, dy, dz, kcap, weighted);          // also selects the KDE sweep and the visit counters
         if (!h->sweep_v1 || dz == 0) { sweep = pick_sweepw(dx, dy, dz, kcap, weighted); windowed = true; }
     }
+    if (euclid && dbg) { sweep = nullptr; strip = nullptr; }        // per-point outputs of umi come from the generic kernel
     if (!sweep && o->path != SCRIBE_PATH_GENERIC && !euclid && kcap) fused = pick_fused(dx, dy, dz, kcap, q, weighted);
     const bool need_points = (fused == nullptr && sweep == nullptr) || dbg != nullptr;
     const int wpj = (n_max + 32 * SWEEP_Q - 1) / (32 * SWEEP_Q);        // warps per job, sweep kernels
     unsigned long long* visited = nullptr;
     if (sweep) {
-        h->visited.ensure(3 * sizeof(unsigned long long));
-        CU(cudaMemsetAsync(h->visited.p, 0, 3 * sizeof(unsigned long long), h->stream));
+        h->visited.ensure(4 * sizeof(unsigned long long));        // kNN / count / KDE visits, umi domain flag
+        CU(cudaMemsetAsync(h->visited.p, 0, 4 * sizeof(unsigned long long), h->stream));
         visited = h->visited.as<unsigned long long>();
     }
 
@@ -433,6 +439,13 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
         }
     }
 
+    if (euclid && sweep) {                                       // umi on the sweep: prefix sums of the weights in y order
+        h->wcum.ensure(sizeof(double) * nj * ((size_t)n_max + 1));
+        weight_prefix_kernel<<<(unsigned)nj, 256, 0, h->stream>>>(dj, h->wcum.as<double>(), (int64_t)n_max + 1);
+        CU(cudaGetLastError());
+        h->st.kernel_launches++;
+    }
+
     // ---- estimator -----------------------------------------------------------------------------------
     if (strip) {
         const int spj = (n_max + STRIP - 1) / STRIP;                 // strips (= warps) per job
@@ -512,8 +525,12 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
     h->st.estimator_ms += ms;
     h->st.jobs += nj;
     if (sweep) {
-        unsigned long long v[3] = {0, 0, 0};
+        unsigned long long v[4] = {0, 0, 0, 0};
         CU(cudaMemcpy(v, h->visited.p, sizeof(v), cudaMemcpyDeviceToHost));
+        if (euclid) {
+            if (v[3] && domain_error) *domain_error = true;
+            if (used_sweep) *used_sweep = true;
+        }
         h->st.visited_knn += (int64_t)v[0]; h->st.visited_count += (int64_t)v[1]; h->st.visited_kde += (int64_t)v[2];
         if (weighted && v[2] == 0 && host_desc) for (int64_t j = 0; j < nj; j++) h->st.visited_kde += (int64_t)hj[j].n * hj[j].n;
     } else if (!n_on_device) {
@@ -581,7 +598,8 @@ void single_job(scribe_handle* h, const double* x, const double* y, const double
         }
         ordered = true;
     }
-    run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom, ordered);
+    bool umi_mean = false;                                   // the sweep returns the mean of the per-point terms, the generic path their sum
+    run_jobs(h, hj, (int)n, dx, dy, dz, o, h->out.as<double>(), false, dbg, &dom, ordered, -1, &umi_mean);
     h->st.point_pairs += n * n;
     double v = 0.0;
     CU(cudaMemcpyAsync(&v, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -591,7 +609,8 @@ void single_job(scribe_handle* h, const double* x, const double* y, const double
         if (dom) fail(SCRIBE_E_DOMAIN, "math domain error");
         // information_estimators.py:264,:274-276
         const double N = (double)n;
-        v = digamma_f64((double)o->k) + 2.0 * std::log(N - 1.0) - digamma_f64(N) + vd_host(dx) + vd_host(dy) - vd_host(dx + dy) - v / N;
+        v = digamma_f64((double)o->k) + 2.0 * std::log(N - 1.0) - digamma_f64(N) + vd_host(dx) + vd_host(dy) - vd_host(dx + dy)
+            - (umi_mean ? v : v / N);
     }
     if (out) *out = v;
 }
@@ -1055,7 +1074,7 @@ void scribe_destroy(scribe_handle* h) {
     for (DevBuf* b : {&h->E, &h->run_off_d, &h->S, &h->Y, &h->psi, &h->jobs, &h->partial, &h->cols, &h->specs, &h->u, &h->r,
                       &h->eps, &h->cnt, &h->wsum, &h->out, &h->flag, &h->idx32a, &h->idx32b, &h->neff, &h->dims, &h->pjobs, &h->single,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->perm, &h->sort_tmp, &h->seg_off, &h->keyspecs, &h->visited, &h->permS, &h->strips, &h->permE, &h->sortedE, &h->rawjobs,
-                      &h->raw0, &h->raw1, &h->stat, &h->nanflag, &h->sorted, &h->rankf, &h->crank, &h->sortedS, &h->rankS, &h->permY, &h->sortedY, &h->rankY, &h->rankE})
+                      &h->raw0, &h->raw1, &h->stat, &h->nanflag, &h->wcum, &h->sorted, &h->rankf, &h->crank, &h->sortedS, &h->rankS, &h->permY, &h->sortedY, &h->rankY, &h->rankE})
         b->release();
     for (DevBuf& b : h->post) b.release();
     cudaEventDestroy(h->ev_call0); cudaEventDestroy(h->ev_call1); cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1);
@@ -1241,6 +1260,82 @@ int scribe_roc(scribe_handle* h, const double* scores, const uint8_t* truth, int
         if (fpr) CU(cudaMemcpyAsync(fpr, x, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, h->stream));
         if (tpr) CU(cudaMemcpyAsync(tpr, y, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, h->stream));
         h->st.kernel_launches += 3; h->st.d2h_bytes += sizeof(double) * (2 * (m + 1) + 1);
+        end_call(h);
+    });
+}
+
+// ---- preprocessing of the resident expression matrix -------------------------------------------------
+int scribe_normalize_resident(scribe_handle* h, int32_t mean_order, int32_t avg_order) {
+    return guarded(h, [&] {
+        if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
+        if ((mean_order | avg_order) & ~1) fail(SCRIBE_E_ARG, "summation order must be 0 (pairwise) or 1 (sequential)");
+        begin_call(h);
+        const int n_runs = (int)h->run_off.size() - 1;
+        h->raw0.ensure(sizeof(double) * h->n_genes * h->n_cells);
+        const int64_t segs = h->n_genes * n_runs;
+        normalize_rows_kernel<<<(unsigned)((segs + 63) / 64), 64, 0, h->stream>>>(h->E.as<double>(), h->n_genes, h->n_cells, h->run_off_d.as<int64_t>(),
+                                                                                 n_runs, mean_order, avg_order, h->raw0.as<double>());
+        CU(cudaGetLastError());
+        h->st.kernel_launches = 1; h->sortE_valid = false;
+        end_call(h);
+    });
+}
+
+int scribe_smooth_resident(scribe_handle* h, int32_t window, int64_t* new_n_cells, int64_t* new_run_offsets) {
+    return guarded(h, [&] {
+        if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
+        if (window < 1) fail(SCRIBE_E_ARG, "window must be >= 1");
+        const int n_runs = (int)h->run_off.size() - 1;
+        std::vector<int64_t> off(n_runs + 1, 0);
+        for (int r = 0; r < n_runs; r++) off[r + 1] = off[r] + std::max<int64_t>(0, h->run_off[r + 1] - h->run_off[r] - (window - 1));
+        const int64_t out_cells = off[n_runs];
+        if (out_cells < 1) fail(SCRIBE_E_LENGTH, "window leaves no cells");
+        begin_call(h);
+        h->raw0.ensure(sizeof(double) * h->n_genes * out_cells); h->raw1.ensure(sizeof(int64_t) * (n_runs + 1));
+        CU(cudaMemcpyAsync(h->raw1.p, off.data(), sizeof(int64_t) * (n_runs + 1), cudaMemcpyHostToDevice, h->stream));
+        const int64_t segs = h->n_genes * n_runs;
+        smooth_rows_kernel<<<(unsigned)((segs + 63) / 64), 64, 0, h->stream>>>(h->E.as<double>(), h->n_genes, h->n_cells, h->run_off_d.as<int64_t>(),
+                                                                              n_runs, window, h->raw0.as<double>(), out_cells, h->raw1.as<int64_t>());
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        std::swap(h->E, h->raw0);                                  // the smoothed matrix becomes the resident one
+        CU(cudaMemcpyAsync(h->run_off_d.p, off.data(), sizeof(int64_t) * (n_runs + 1), cudaMemcpyHostToDevice, h->stream));
+        h->n_cells = out_cells; h->run_off = off; h->sortE_valid = false;
+        if (new_n_cells) *new_n_cells = out_cells;
+        if (new_run_offsets) std::memcpy(new_run_offsets, off.data(), sizeof(int64_t) * (n_runs + 1));
+        h->st.kernel_launches = 1; h->st.h2d_bytes = 2 * sizeof(int64_t) * (n_runs + 1);
+        end_call(h);
+    });
+}
+
+int scribe_read_matrix(scribe_handle* h, int64_t gene0, int64_t n_genes, double* out) {
+    return guarded(h, [&] {
+        if (h->n_genes == 0) fail(SCRIBE_E_STATE, "no expression matrix uploaded");
+        if (gene0 < 0 || n_genes < 1 || gene0 + n_genes > h->n_genes || !out) fail(SCRIBE_E_ARG, "bad row range");
+        begin_call(h);
+        CU(cudaMemcpyAsync(out, h->E.as<double>() + (size_t)gene0 * h->n_cells, sizeof(double) * n_genes * h->n_cells, cudaMemcpyDeviceToHost, h->stream));
+        h->st.d2h_bytes = sizeof(double) * n_genes * h->n_cells;
+        end_call(h);
+    });
+}
+
+int scribe_knn_regress(scribe_handle* h, const double* px, const double* py, const double* value, int64_t n,
+                       const double* qx, const double* qy, int64_t m, int32_t k, double* out) {
+    return guarded(h, [&] {
+        if (!px || !py || !value || !qx || !qy || !out || n < 1 || m < 1) fail(SCRIBE_E_ARG, "empty kNN regression");
+        if (k < 1 || k + 1 > KNN_REG_MAXK) fail(SCRIBE_E_ARG, "k must be in [1, 15]");
+        begin_call(h);
+        h->post[0].ensure(sizeof(double) * 3 * n); h->post[1].ensure(sizeof(double) * 3 * m);
+        double* d = h->post[0].as<double>(); double* qd = h->post[1].as<double>();
+        CU(cudaMemcpyAsync(d, px, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(d + n, py, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(d + 2 * n, value, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(qd, qx, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(qd + m, qy, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+        knn_regress_kernel<<<(unsigned)((m * 32 + 127) / 128), 128, 0, h->stream>>>(d, d + n, d + 2 * n, n, qd, qd + m, m, k, qd + 2 * m);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, qd + 2 * m, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        h->st.h2d_bytes = sizeof(double) * (3 * n + 2 * m); h->st.d2h_bytes = sizeof(double) * m; h->st.kernel_launches = 1;
         end_call(h);
     });
 }

@@ -1,11 +1,17 @@
 // kernels.cuh -- sm_100a device code of the KSG hot path.
 //
-// Everything here computes in FP64 on purpose.  The reference (scipy cKDTree, float64) decides ball
+// Everything that decides a neighbour COUNT computes in FP64 on purpose (two documented exceptions below).  The reference
+// (scipy cKDTree, float64) decides ball
 // membership with `max_c |a_c - b_c| <= eps_i` where eps_i is itself such a difference, so neighbour
 // counts are only reproducible bit-for-bit if the differences and comparisons are done in float64.
 // B200 (unlike B300) keeps a real FP64 pipe: measured 64 lanes/clk/SM for DADD/DSETP
 // (tools/microbench.cu -> profiles/microbench_r1.jsonl), i.e. half the FP32 FADD rate, which makes the
 // exact path only ~1.4x slower than an (inexact) FP32 one -- see DESIGN.md "Why FP64".
+// Exceptions, neither of which can change a count: (1) the KDE kernels (kde_kernel, kde_sweep_kernel) form the squared
+// distance in FP64 but evaluate 2^x with ex2.approx.ftz.f32 and accumulate each chunk's terms in FP32 -- the uniformisation
+// weights are then good to ~2e-6 relative, inside the 1e-5 budget of umi/cumi values (tests hold them to 1e-6); (2) the
+// windowed sweep (sweep_window.cuh) pre-filters k-NN candidates in FP32 with a bound that makes the marked set a superset of
+// the exact one, every marked candidate being re-tested in FP64.
 //
 // Layout: a "job" is one estimator evaluation on N points of joint dimension D = dx+dy+dz.  Its columns
 // live dimension-major in HBM (D pointers to N contiguous doubles, JobDesc).  A CTA owns a block of
@@ -41,6 +47,7 @@ struct JobDesc {
     const double* srt[4];     //   the values of that coordinate in ascending order (srt_n[c] of them): the ball |q_c - v| <= eps is one
     const float*  rk[4];      //   rank range of it; rk[c][row] = position of the job's row in that order (an integer < 2^22, as float)
     int32_t srt_n[4];         //   (srt_n may exceed n: dynamics coupling ranks a job's kept cells among ALL cells of the gene)
+    const double* wcum;       // umi on the sweep: exclusive prefix sums of the weights in sweep (y) order, n + 1 values
 };
 
 struct PointOut {             // optional per-point outputs (debug entry point, generic path, kNN-only mode)
@@ -1539,6 +1546,35 @@ __global__ void rank_from_perm_kernel(const int32_t* __restrict__ perm, const in
     }
 }
 
+// wcum[job][r] = w[perm[0]] + ... + w[perm[r-1]]  (r = 0..n): prefix sums of a job's weights in sweep order; one CTA per job,
+// tiles of 256 ranks scanned in order (deterministic)
+__global__ void __launch_bounds__(256)
+weight_prefix_kernel(JobDesc* __restrict__ jobs, double* __restrict__ wcum, int64_t stride)
+{
+    __shared__ double wtot[8];
+    __shared__ double carry;
+    JobDesc& jd = jobs[blockIdx.x];
+    const int n = jd.n;
+    double* out = wcum + (size_t)blockIdx.x * stride;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { carry = 0.0; out[0] = 0.0; jd.wcum = out; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 256) {
+        const int r = base + tid;
+        double v = (r < n) ? jd.w[jd.perm ? jd.perm[r] : r] : 0.0;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) wtot[wid] = v;
+        __syncthreads();
+        double off = carry;
+        for (int w = 0; w < wid; w++) off += wtot[w];
+        if (r < n) out[r + 1] = off + v;
+        __syncthreads();
+        if (tid == 255) carry = off + v;
+        __syncthreads();
+    }
+}
+
 // out[job] = (sum of that job's CTA partials, in CTA order) / n      (np.mean at :109,:173,:403)
 __global__ void finalize_mean_kernel(const JobDesc* __restrict__ jobs, const double* __restrict__ partial,
                                      int blocks_per_job, int n_jobs, double* __restrict__ out)
@@ -1813,7 +1849,7 @@ build_rdi_jobs_kernel(const RawJob* __restrict__ raw, int64_t n_jobs, JobDesc* _
     jd.strip = nullptr; jd.npad = 0;
     jd.qoff = j * n_max;
     jd.n = lay.n_of[di]; jd.pad = 0;
-    jd.absmax = 0.0;
+    jd.absmax = 0.0; jd.wcum = nullptr;
     #pragma unroll
     for (int c = 0; c < 4; c++) { jd.srt[c] = nullptr; jd.rk[c] = nullptr; jd.srt_n[c] = 0; }
     if (sorted) {                                    // rank-space count pass: x of the source, y of the target

@@ -108,6 +108,82 @@ coupling_normalise_kernel(double* __restrict__ S, double* __restrict__ V, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
+// causal_model.normalize (causal_network.py:104-109) on the resident matrix: every (gene, run) row becomes
+// (v - mean) / std(ddof = 1), NaN -> 0.  pandas forms the two statistics with different summation orders depending on its
+// version and the frame's memory layout, so both orders are implemented (0 = numpy pairwise, 1 = sequential) and the host
+// picks the pair that reproduces pandas on a few probe rows (and falls back to pandas itself when none does).
+//   mean        = sum_{order m}(v) / n
+//   avg         = sum_{order a}(v) / n ;  std = sqrt( sum_{pairwise}((avg - v)^2) / (n - 1) )      (pandas nanops.nanvar)
+// One thread per (gene, run) segment: the sums are sequential by definition.
+// ------------------------------------------------------------------------------------------------
+__device__ inline double ordered_sum(const double* a, int64_t n, int order)
+{
+    if (order == 0) return np_pairwise_sum(a, n);
+    double s = 0.0;
+    for (int64_t i = 0; i < n; i++) s += a[i];
+    return s;
+}
+
+__global__ void normalize_rows_kernel(double* __restrict__ E, int64_t n_genes, int64_t n_cells, const int64_t* __restrict__ run_off, int n_runs,
+                                      int mean_order, int avg_order, double* __restrict__ scratch)
+{
+    const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_genes * n_runs) return;
+    const int64_t g = seg / n_runs; const int r = (int)(seg - g * n_runs);
+    const int64_t n = run_off[r + 1] - run_off[r];
+    if (n <= 0) return;
+    double* v = E + g * n_cells + run_off[r];
+    double* sq = scratch + g * n_cells + run_off[r];
+    const double mean = ordered_sum(v, n, mean_order) / (double)n;
+    const double avg = ordered_sum(v, n, avg_order) / (double)n;
+    for (int64_t i = 0; i < n; i++) { const double d = avg - v[i]; sq[i] = d * d; }
+    const double sd = sqrt(np_pairwise_sum(sq, n) / (double)(n - 1));
+    for (int64_t i = 0; i < n; i++) { const double z = (v[i] - mean) / sd; v[i] = (z != z) ? 0.0 : z; }
+}
+
+// causal_model.smooth (causal_network.py:97-101): rolling mean of `w` cells along every (gene, run) row, pandas' online
+// algorithm (pandas/_libs/window/aggregations.pyx roll_mean): Kahan-compensated running sum with separate compensation terms
+// for the values entering and leaving the window, leaving before entering; a window of identical values returns that value;
+// a window without negatives never returns a negative mean (and vice versa).  The first w - 1 positions of a row have no
+// full window: dropna(axis=1, how="all") removes those columns, so every run shrinks by w - 1 cells in the output layout.
+__global__ void smooth_rows_kernel(const double* __restrict__ E, int64_t n_genes, int64_t n_cells, const int64_t* __restrict__ run_off, int n_runs,
+                                   int w, double* __restrict__ out, int64_t out_cells, const int64_t* __restrict__ out_off)
+{
+    const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_genes * n_runs) return;
+    const int64_t g = seg / n_runs; const int r = (int)(seg - g * n_runs);
+    const int64_t n = run_off[r + 1] - run_off[r];
+    if (n < w) return;
+    const double* v = E + g * n_cells + run_off[r];
+    double* o = out + g * out_cells + out_off[r];
+    double sum_x = 0.0, c_add = 0.0, c_rem = 0.0, prev = v[0];
+    int64_t nobs = 0, neg = 0, same = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (i >= w) {                                            // remove_mean(values[i - w])
+            const double val = v[i - w];
+            const double y = -val - c_rem, t = sum_x + y;
+            c_rem = t - sum_x - y; sum_x = t;
+            nobs--; if (signbit(val)) neg--;
+        }
+        {                                                        // add_mean(values[i])
+            const double val = v[i];
+            const double y = val - c_add, t = sum_x + y;
+            c_add = t - sum_x - y; sum_x = t;
+            nobs++; if (signbit(val)) neg++;
+            same = (val == prev) ? same + 1 : 1;
+            prev = val;
+        }
+        if (i >= w - 1) {                                        // calc_mean
+            double res = sum_x / (double)nobs;
+            if (same >= nobs) res = prev;
+            else if (neg == 0 && res < 0) res = 0;
+            else if (neg == nobs && res > 0) res = 0;
+            o[i - (w - 1)] = res;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CLR (Scribe.py:142-176): z-scores of round(M, 10) against the row (and column) mean / std (ddof = 1) of M, negatives
 // clipped to 0, combined as sqrt((z_row^2 + z_col^2) / 2).  The reference subtracts the row statistics without a keepdims
 // axis when M is square, so for square M element (i, j) is z-scored against the statistics of ROW j (Scribe.py:151-154);
@@ -219,6 +295,74 @@ roc_curve_kernel(const int32_t* __restrict__ tp, const int32_t* __restrict__ fp,
             const double xp = (double)fp[i - 1] / fmax_, yp = (double)tp[i - 1] / tmax_;
             area_terms[i - 1] = fabs((xi - xp) * (yi + yp) / 2.0);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN grid regressor of viz_causality / viz_comb_logic (Scribe/plot/heatmaps.py:405-423, :578-596): for every query point
+// (a grid_num x grid_num mesh, 625 by default) the k+1 nearest data points in the Euclidean plane (cKDTree.query(q, k+1)),
+// the nearest one dropped, weights u = exp(-d / min d) normalised to 1, result = sum w * value[neighbour].
+// One warp per query: every lane keeps the k+1 best of its stride of the data points, then the warp merges the 32 lists
+// by k+1 rounds of arg-min.  Distances as scipy forms them: sqrt(dx*dx + dy*dy), no FMA.  Ties in distance resolve to the
+// lower point index (the reference inherits whatever order the kd-tree traversal gives them).
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN_REG_MAXK = 16;      // k + 1 <= 16
+
+__global__ void __launch_bounds__(128)
+knn_regress_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ value, int64_t n,
+                   const double* __restrict__ qx, const double* __restrict__ qy, int64_t m, int k, double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= m) return;
+    const int kk = k + 1;
+    const double x0 = qx[q], y0 = qy[q];
+    double bd[KNN_REG_MAXK]; int64_t bi[KNN_REG_MAXK];
+    #pragma unroll
+    for (int t = 0; t < KNN_REG_MAXK; t++) { bd[t] = INFINITY; bi[t] = -1; }
+    for (int64_t j = lane; j < n; j += 32) {
+        const double dx = x0 - px[j], dy = y0 - py[j];
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d2 < bd[KNN_REG_MAXK - 1] || (kk < KNN_REG_MAXK && d2 < bd[kk - 1])) {
+            // insertion into the lane's ascending list of kk entries (indices ascend within equal distances: j only grows)
+            #pragma unroll
+            for (int t = KNN_REG_MAXK - 1; t >= 0; --t) {
+                if (t < kk) {
+                    const bool here = d2 < bd[t] && (t == 0 || !(d2 < bd[t - 1]));
+                    const bool shift = t > 0 && d2 < bd[t - 1];
+                    if (shift) { bd[t] = bd[t - 1]; bi[t] = bi[t - 1]; }
+                    else if (here) { bd[t] = d2; bi[t] = j; }
+                }
+            }
+        }
+    }
+    // merge: kk rounds; each round the warp takes the smallest head (ties: lower index) and that lane pops it
+    double nd[KNN_REG_MAXK]; double nv[KNN_REG_MAXK];
+    int head = 0;
+    for (int r = 0; r < kk; r++) {
+        double hd = INFINITY; int64_t hi = INT64_MAX;
+        #pragma unroll
+        for (int t = 0; t < KNN_REG_MAXK; t++) if (t == head) { hd = bd[t]; hi = bi[t] < 0 ? INT64_MAX : bi[t]; }
+        if (head >= kk) { hd = INFINITY; hi = INT64_MAX; }
+        double md = hd; int64_t mi = hi;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, md, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+        }
+        if (hi == mi && mi != INT64_MAX) head++;
+        nd[r] = (mi == INT64_MAX) ? INFINITY : sqrt(md);        // cKDTree pads missing neighbours with inf
+        nv[r] = (mi == INT64_MAX) ? 0.0 : value[mi];
+    }
+    if (lane == 0) {
+        // heatmaps.py:412-416: neighbours 1..k (the nearest is dropped), u = exp(-d / min d), w = u / sum u, sum(w * value)
+        double dmin = INFINITY;
+        for (int r = 1; r < kk; r++) dmin = fmin(dmin, nd[r]);
+        double su = 0.0, acc = 0.0, u[KNN_REG_MAXK];
+        for (int r = 1; r < kk; r++) { u[r] = exp(-nd[r] / dmin); su += u[r]; }
+        for (int r = 1; r < kk; r++) acc += (u[r] / su) * nv[r];
+        out[q] = acc;
     }
 }
 

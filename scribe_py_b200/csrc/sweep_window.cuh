@@ -190,7 +190,12 @@ __global__ void __launch_bounds__(SWEEP_TPB, SWEEPW_MIN_CTAS)
 ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, const double* __restrict__ psi_tab,
                   double* __restrict__ partial, PointOut po, unsigned long long* __restrict__ visited)
 {
-    static_assert(DZ >= 0 && DZ <= 3 && !(DZ == 0 && WEIGHTED), "0..3 conditioning columns; DZ = 0 is mi(x, y): sorted by y");
+    static_assert(DZ >= 0 && DZ <= 3, "0..3 conditioning columns; DZ = 0 is mi(x, y), or umi(x, y) when WEIGHTED: sorted by y");
+    // umi (information_estimators.py:209-277): EUCLIDEAN joint k-NN (the list holds squared distances d2 = dx^2 + dy^2, formed
+    // without FMA as scipy does), r = sqrt(d2_k), balls by scipy's squared-radius test diff^2 <= fl(r * r) (:263-273).  Both
+    // marginal balls are rank ranges of a sorted column, so there is no count scan at all: n_x = range in the sorted x column,
+    // W_y = difference of two prefix sums of the weights in y order (JobDesc.wcum).
+    constexpr bool UMI = DZ == 0 && WEIGHTED;
     constexpr int D   = 2 + DZ;
     constexpr int KEY = D - 1;
     constexpr int NP  = D - 1;                    // non-key coordinates: x, y, z_0 .. z_{DZ-2}
@@ -269,6 +274,24 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         for (int t = 0; t < KL; t++) L[q][t] = (t < KL - k) ? -INFINITY : INFINITY;
     const double slack = jd.absmax * 0x1p-22 + 1e-37;           // +inf when the job's scale is not FP32-safe: everything is marked
 
+    // FP32 bound of the pre-filter from the current bar (a distance; for umi a squared distance: the bound applies to |dx|)
+    auto bound32 = [&](double bar) {
+        const double lin = UMI ? __dsqrt_ru(bar) : bar;
+        return __double2float_ru(__dadd_ru(__dmul_ru(lin, 1.0 + 0x1p-22), slack));
+    };
+    // exact joint distance of a query and staged candidate j: Chebyshev maximum, or for umi the squared Euclidean distance
+    auto exact_dist = [&](int q, int j) {
+        if constexpr (UMI) {
+            const double dx = qc[q][0] - bd[j][0], dy = qc[q][KEY] - bk[j];
+            return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        } else {
+            double dd = abs_f64(qc[q][KEY] - bk[j]);
+            #pragma unroll
+            for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
+            return dd;
+        }
+    };
+
     // selfq: slot whose own points are the staged chunk (its lane-th candidate is the query itself and is skipped), or -1;
     // fine: insert after every block of UNR candidates instead of once per chunk (centre chunks: the bar drops fast there)
     auto knn_body = [&](auto q_first, int selfq, bool fine) {
@@ -276,7 +299,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         unsigned mask[Q];
         float T[Q];
         #pragma unroll
-        for (int q = 0; q < Q; q++) { mask[q] = 0u; T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack)); }
+        for (int q = 0; q < Q; q++) { mask[q] = 0u; T[q] = bound32(L[q][KL - 1]); }
         // blocks of UNR candidates: bits are set with immediates inside a block and shifted into place once per block
         // (a fully unrolled scan does not fit the instruction cache next to the other phases: ncu no_inst 37 %)
         #pragma unroll 1
@@ -324,9 +347,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                     const int j = has ? __ffs(mask[q]) - 1 : 0;
                     mask[q] &= mask[q] - 1;                                    // 0 stays 0
                     any |= mask[q];
-                    double dd = abs_f64(qc[q][KEY] - bk[j]);
-                    #pragma unroll
-                    for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
+                    const double dd = exact_dist(q, j);
                     if (has && dd < L[q][KL - 1]) topk_insert<KL>(L[q], dd);   // exact test; NaN (padding) never passes
                 }
             }
@@ -337,16 +358,14 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                 while (mask[q]) {
                     const int j = __ffs(mask[q]) - 1;
                     mask[q] &= mask[q] - 1;
-                    double dd = abs_f64(qc[q][KEY] - bk[j]);
-                    #pragma unroll
-                    for (int d = 0; d < NP; d++) { const double a = abs_f64(qc[q][d] - bd[j][d]); dd = (a > dd) ? a : dd; }
+                    const double dd = exact_dist(q, j);
                     if (dd < L[q][KL - 1]) topk_insert<KL>(L[q], dd);          // exact test; NaN (padding) never passes
                 }
             }
 #endif
             if (fine) {
                 #pragma unroll
-                for (int q = Q0; q < Q; q++) T[q] = __double2float_ru(__dadd_ru(__dmul_ru(L[q][KL - 1], 1.0 + 0x1p-22), slack));
+                for (int q = Q0; q < Q; q++) T[q] = bound32(L[q][KL - 1]);
             }
         }
     };
@@ -429,7 +448,10 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         auto need = [&](double znext) {
             unsigned f = 0u;
             #pragma unroll
-            for (int q = 0; q < Q; q++) f |= (fabs(qc[q][KEY] - znext) < L[q][KL - 1]) ? (1u << q) : 0u;
+            for (int q = 0; q < Q; q++) {
+                const double dk = qc[q][KEY] - znext;
+                f |= ((UMI ? __dmul_rn(dk, dk) : fabs(dk)) < L[q][KL - 1]) ? (1u << q) : 0u;
+            }
             return f;
         };
         while (true) {
@@ -449,9 +471,13 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         }
     }
 
-    double eps[Q];
+    double eps[Q], rad[Q];                                         // rad: what a coordinate difference is tested against
     #pragma unroll
-    for (int q = 0; q < Q; q++) eps[q] = L[q][KL - 1];
+    for (int q = 0; q < Q; q++) {
+        eps[q] = L[q][KL - 1]; rad[q] = eps[q];
+        if (UMI) { eps[q] = __dsqrt_rn(eps[q]); rad[q] = __dmul_rn(eps[q], eps[q]); }      // scipy: r = sqrt(d2_k); ball test diff^2 <= r * r
+    }
+    auto inball = [&](double diff, int q) { return UMI ? (__dmul_rn(diff, diff) <= rad[q]) : (fabs(diff) <= rad[q]); };
 
     // ---------------- pass 2: rank windows, then x / y (/ extra z) bits per candidate ----------------
     int lo[Q], hi[Q];
@@ -469,13 +495,13 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                 if (la[q] < lb[q]) {
                     const int mid = (la[q] + lb[q]) >> 1;
                     const double zr = kcol[perm ? perm[mid] : mid];
-                    const bool A = (zr > qc[q][KEY]) || (fabs(qc[q][KEY] - zr) <= eps[q]);
+                    const bool A = (zr > qc[q][KEY]) || inball(qc[q][KEY] - zr, q);
                     if (A) lb[q] = mid; else la[q] = mid + 1;
                 }
                 if (ha[q] < hb[q]) {
                     const int mid = (ha[q] + hb[q]) >> 1;
                     const double zr = kcol[perm ? perm[mid] : mid];
-                    const bool B = (zr < qc[q][KEY]) || (fabs(qc[q][KEY] - zr) <= eps[q]);
+                    const bool B = (zr < qc[q][KEY]) || inball(qc[q][KEY] - zr, q);
                     if (B) ha[q] = mid + 1; else hb[q] = mid;
                 }
             }
@@ -495,13 +521,13 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
                 if (la[q] < lb[q]) {
                     const int mid = (la[q] + lb[q]) >> 1;
                     const double xr = sv[mid];
-                    const bool A = (xr > v[q]) || (fabs(v[q] - xr) <= eps[q]);
+                    const bool A = (xr > v[q]) || inball(v[q] - xr, q);
                     if (A) lb[q] = mid; else la[q] = mid + 1;
                 }
                 if (ha[q] < hb[q]) {
                     const int mid = (ha[q] + hb[q]) >> 1;
                     const double xr = sv[mid];
-                    const bool B = (xr < v[q]) || (fabs(v[q] - xr) <= eps[q]);
+                    const bool B = (xr < v[q]) || inball(v[q] - xr, q);
                     if (B) ha[q] = mid + 1; else hb[q] = mid;
                 }
             }
@@ -718,7 +744,9 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     };
 
     unsigned long long nvis2 = 0;
-    if constexpr (RANKED) {
+    if constexpr (UMI) {
+        // nothing to scan: both marginal balls are rank ranges
+    } else if constexpr (RANKED) {
         RChunk nxt = load_rchunk(cmin), cur;
         for (int c = cmin; c <= cmax; c++) {
             cur = nxt;
@@ -753,7 +781,16 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         if (qok[q]) {
             const int a = nxyz[q] - 1, b = nxz[q] - 1, c = nyz[q] - 1, d = nz[q] - 1;
             const int64_t o = jd.qoff + qidx[q];
-            if (DZ == 0) {
+            if (UMI) {
+                // information_estimators.py:268-276: n_x = |ball_x| - 1, W_y = sum of the weights over ball_y minus w_i;
+                // term = w_i * log(n_x) + w_i * log(W_y); math.log raises for arguments <= 0 -> domain flag (visited[3])
+                const double wi = qw[q];
+                const int nx = nxm[q] - 1;
+                const double Wy = (jd.wcum[hi[q] + 1] - jd.wcum[lo[q]]) - wi;
+                if ((nx <= 0 || Wy <= 0.0) && visited) atomicOr(reinterpret_cast<unsigned int*>(visited + 3), 1u);
+                acc += wi * log((double)nx) + wi * log(Wy);
+                if (po.wsum) { po.wsum[2 * o] = Wy; po.wsum[2 * o + 1] = 0.0; }
+            } else if (DZ == 0) {
                 // information_estimators.py:102-107: psi(N) + psi(n_xy) - psi(n_x) - psi(n_y); slots as in the dense kernel
                 acc += psi_int(psi_tab, n) + psi_int(psi_tab, b) - psi_int(psi_tab, nxm[q] - 1) - psi_int(psi_tab, d);
             } else if (WEIGHTED) {
@@ -767,7 +804,8 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             if (po.eps) po.eps[o] = eps[q];
             if (po.cnt) {
                 int32_t* oc = po.cnt + 4 * o;
-                if (DZ == 0) { oc[0] = b; oc[1] = nxm[q] - 1; oc[2] = d; oc[3] = n - 1; }      // n_xy, n_x, n_y, (all)
+                if (UMI)          { oc[0] = -1; oc[1] = nxm[q] - 1; oc[2] = d; oc[3] = n - 1; }  // (joint ball not counted), n_x, n_y, (all)
+                else if (DZ == 0) { oc[0] = b; oc[1] = nxm[q] - 1; oc[2] = d; oc[3] = n - 1; }  // n_xy, n_x, n_y, (all)
                 else         { oc[0] = a; oc[1] = b; oc[2] = c; oc[3] = d; }
             }
         }

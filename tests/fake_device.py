@@ -11,9 +11,17 @@ class FakeHandle:
     def __init__(self):
         self.calls = []
 
+    resident_token = 0
+
     def upload_matrix(self, E, run_offsets=None):
         self.E = np.asarray(E, dtype=float)
         self.ro = np.array([0, self.E.shape[1]]) if run_offsets is None else np.asarray(run_offsets)
+        self.uploads = getattr(self, "uploads", 0) + 1
+        self.resident_token += 1
+        return self.resident_token
+
+    def read_matrix(self, gene0=0, n_genes=None):
+        return self.E[gene0:None if n_genes is None else gene0 + n_genes].copy()
 
     def _runs(self, g):
         return [self.E[g, self.ro[r]:self.ro[r + 1]] for r in range(len(self.ro) - 1)]

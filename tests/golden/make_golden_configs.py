@@ -185,6 +185,29 @@ def part_post(procs):
     out["edges_in"] = W
     out["edges_src"] = np.array([names8.index(s) for s in top["source"]]); out["edges_dst"] = np.array([names8.index(s) for s in top["target"]])
     out["edges_w"] = top["weight"].to_numpy(dtype=float)
+    # kNN grid regressor of viz_causality (plot/heatmaps.py:389-423), the reference's own statements and scipy calls on one gene
+    # pair: x(t - d), y(t), z = y(t - 1); grid over (x, z); tree over the (x, y) columns (as the reference builds it);
+    # k + 1 neighbours, the nearest dropped, u = exp(-d / min d); expected_y normalised by its maximum
+    import scipy.spatial as ss
+    E = recipes.rdi_synthetic(6, 700, 9)
+    delay, k, grid_num = 1, 5, 25
+    x = [i for i in E[0]]; y_ori = [i for i in E[1]]
+    x = x[:-delay]; y = y_ori[delay:]; z = y_ori[delay - 1:-1]
+    cur_data = pd.DataFrame({'x': x, 'y': y, 'z': z, 'pair': 'a->b'})
+    x_meshgrid = np.linspace(min(x), max(x), grid_num, endpoint=True)
+    z_meshgrid = np.linspace(min(z), max(z), grid_num, endpoint=True)
+    xv, zv = np.meshgrid(x_meshgrid, z_meshgrid)
+    xp = xv.reshape((1, -1)).tolist(); zp = zv.reshape((1, -1)).tolist()
+    xz_query = np.array(xp + zp).T
+    tree_xz = ss.cKDTree(cur_data[['x', 'y']])
+    dist_mat, idx_mat = tree_xz.query(xz_query, k=k + 1)
+    exp_y = np.empty(len(dist_mat))
+    for i in range(dist_mat.shape[0]):
+        subset_dat = cur_data.iloc[idx_mat[i, 1:], 1]
+        u = np.exp(-dist_mat[i, 1:] / np.min(dist_mat[i, 1:]))
+        w = u / np.sum(u)
+        exp_y[i] = sum(np.array(w) * np.array(subset_dat))
+    out["knnreg_query"] = xz_query; out["knnreg_raw"] = exp_y.copy(); out["knnreg_norm"] = exp_y / max(exp_y)
     return out
 
 

@@ -669,6 +669,88 @@ def test_post_processing_on_device(S, golden_configs, tmp_path):
     assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and ga == pytest.approx(ra, abs=1e-15)
 
 
+def test_normalize_smooth_on_device(S, golden_configs):
+    """causal_model.normalize / .smooth on the matrix resident on the GPU: bit-identical to the reference's pandas results
+    (causal_network.py:97-109); the NaN-padded multi-run frame takes the pandas path and gives the same numbers"""
+    g = golden_configs
+    E = g["norm_in"]
+    names = ["g%d" % i for i in range(6)]
+    h = S._lib.default_handle()
+    m = S.causal_model(pd.DataFrame(E, index=pd.Index(names, name="GENE_ID")))
+    m.normalize()
+    assert m._expr_stale                                       # ran on the device: the frame is rebuilt on first read
+    assert np.array_equal(m.expression.to_numpy(dtype=float), g["norm_out"])
+    for w in (3, 7):
+        m = S.causal_model(pd.DataFrame(E, index=pd.Index(names, name="GENE_ID")))
+        m.smooth(w)
+        assert m._expr_stale
+        assert np.array_equal(m.expression.to_numpy(dtype=float), g["smooth%d_out" % w])
+        assert np.array_equal(np.asarray(m.expression.columns, dtype=np.int64), g["smooth%d_cols" % w])
+    runs, g6, _ = recipes.gv_e()
+    mm = S.causal_model(recipes.multi_run_frame(runs, g6))
+    mm.normalize()
+    assert np.allclose(mm.expression.to_numpy(dtype=float), g["norm_multi_out"], atol=0, rtol=0, equal_nan=True)
+    # larger panel: every row against pandas, then rdi on the resident normalised matrix == rdi on the pandas-normalised frame
+    E = recipes.ar_panel(40, 3000, 11)[:12]
+    frame = pd.DataFrame(E, index=pd.Index(["g%02d" % i for i in range(12)], name="GENE_ID"))
+    want = frame.sub(frame.mean(axis=1), axis=0).div(frame.std(axis=1), axis=0).fillna(0)
+    m = S.causal_model(frame)
+    m.normalize()
+    assert m._expr_stale
+    r = m.rdi([1, 5])
+    st = h.stats()
+    assert st["h2d_bytes"] < 64 * 1024                          # job table only: the matrix was uploaded once, before normalize()
+    assert np.array_equal(m.expression.to_numpy(dtype=float), want.to_numpy(dtype=float))
+    r2 = S.causal_model(want).rdi([1, 5])
+    for d in (1, 5):
+        assert np.array_equal(r[d].to_numpy(dtype=float), r2[d].to_numpy(dtype=float), equal_nan=True)
+
+
+@pytest.mark.parametrize("density", ["kde", "knn"])
+@pytest.mark.parametrize("k", [3, 5, 10])
+def test_umi_sweep_against_oracle_and_generic(S, k, density):
+    """umi on the Euclidean variant of the windowed sweep (no count scan: n_x and W_y are rank ranges) against the oracle and
+    against the generic thread-per-query kernel, continuous and tied data, N on both sides of the chunk boundaries"""
+    for n, seed, ties in ((300, 1, False), (1000, 2, False), (4097, 3, False), (2500, 4, True)):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n, 1)); y = 0.6 * x + 0.8 * rng.standard_normal((n, 1))
+        if ties:
+            x = np.round(x, 1); y = np.round(y, 2)
+        kw = dict(k=k, density_estimation_method=density, bw=0.2)
+        try:
+            ref = o.umi(x, y, **kw)
+        except ValueError:
+            ref = None
+        for path in ("sweep", "generic"):
+            opts_path = {"sweep": S._lib.PATH_SWEEP, "generic": S._lib.PATH_GENERIC}[path]
+            h = S._lib.default_handle()
+            opts = S._lib.make_opts(S._lib.EST_UMI, k, density, 5, 0.2, path=opts_path)
+            if ref is None:
+                with pytest.raises(ValueError):
+                    h.estimate(x, y, None, opts)
+            else:
+                assert abs(h.estimate(x, y, None, opts) - ref) <= TOL_KDE, (n, path)
+
+
+def test_knn_grid_regressor(S, golden_configs):
+    """the 625-query kNN grid regressor of viz_causality (plot/heatmaps.py:389-428) against the reference's own scipy calls"""
+    E = recipes.rdi_synthetic(6, 700, 9)
+    t = S.heatmaps.causality_grid(E[0], E[1], delay=1, k=5, grid_num=25)
+    assert np.array_equal(np.stack([t["x"], t["z"]], axis=1), golden_configs["knnreg_query"])
+    assert np.allclose(t["expected_y"], golden_configs["knnreg_norm"], atol=1e-12, rtol=0)
+    raw = S.heatmaps.causality_grid(E[0], E[1], delay=1, k=5, grid_num=25, normalized=False)
+    assert np.allclose(raw["expected_y"], golden_configs["knnreg_raw"], atol=1e-12, rtol=0)
+    # brute-force check of the neighbour selection on other k and a triple
+    rng = np.random.default_rng(4)
+    x, y, z = rng.standard_normal(900), rng.standard_normal(900), rng.standard_normal(900)
+    g = S.heatmaps.comb_logic_grid(x, y, z, k=7, grid_num=11, normalized=False)
+    d = np.sqrt((g["x"].to_numpy()[:, None] - x[None, :]) ** 2 + (g["y"].to_numpy()[:, None] - y[None, :]) ** 2)
+    idx = np.argsort(d, axis=1, kind="stable")[:, 1:8]
+    dd = np.take_along_axis(d, idx, axis=1)
+    u = np.exp(-dd / dd.min(axis=1, keepdims=True)); w = u / u.sum(axis=1, keepdims=True)
+    assert np.allclose(g["expected_z"], (w * z[idx]).sum(axis=1), atol=1e-12, rtol=0)
+
+
 def test_multi_gpu_invariance_torchrun():
     """sharded == unsharded, bit for bit, on every GPU count this box offers (tools/check_multi_gpu.py under torchrun)"""
     import os, subprocess, sys

@@ -105,6 +105,25 @@ def test_post_processing_against_reference(S, golden_configs, tmp_path):
     assert got == ref                                     # equal weights (the reciprocal tie) may come in either order
 
 
+def test_matrix_stays_resident_between_calls(S):
+    """rdi() uploads the matrix once; a second rdi()/crdi() on the unchanged model reuses it; assigning a frame re-uploads"""
+    X, genes, delays = recipes.gv_d()
+    m = S.causal_model(pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID")))
+    fake = S._fake
+    m.rdi(delays); n1 = fake.uploads
+    m.rdi([1]); m.crdi(L=1)
+    assert fake.uploads == n1
+    m.expression = pd.DataFrame(X * 2.0, index=pd.Index(genes, name="GENE_ID"))
+    m.rdi([1])
+    assert fake.uploads == n1 + 1
+    other = S.causal_model(pd.DataFrame(X, index=pd.Index(genes, name="GENE_ID")))
+    other.rdi([1])                                        # another model takes the device over ...
+    m.rdi([1])                                            # ... so this one uploads again
+    assert fake.uploads == n1 + 3
+    m.normalize()                                         # host path with the test double (no device normalisation)
+    assert np.allclose(m.expression.to_numpy().mean(axis=1), 0, atol=1e-12)
+
+
 def test_slab_partition():
     from scribe_py_b200.distributed import slab
     for n in (0, 1, 7, 8, 29700, 249500):

@@ -14,7 +14,6 @@ frame = pd.DataFrame(E, index=pd.Index(["g%03d" % i for i in range(G)], name="GE
 model = S.causal_model(frame)
 plan = model._rdi_plan(DELAYS)
 h = S._lib.default_handle()
-h.upload_matrix(plan["E"], plan["run_off"])
 for _ in range(3):
     model._rdi_execute(plan)
 torch.cuda.synchronize()
