@@ -300,11 +300,13 @@ def ours_arm(args):
     n_gpus = world
 
     import recipes
+    ad, spl, vel, genes = c3_adata()
+    if world == 1 and not args.no_cpu:
+        cpu_pool(os.cpu_count() or 1, spl, vel, genes)              # fork the CPU-arm workers before this process touches CUDA
     import scribe_py_b200 as S
     from scribe_py_b200 import Scribe as SC
     from scribe_py_b200 import distributed as D
     h = S._lib.default_handle()
-    ad, spl, vel, genes = c3_adata()
     plan = SC._coupling_plan(ad)
     n_jobs = len(plan["src"])
     SC._upload_layers(h, ad, plan["genes"], "spliced", "velocity", True)
@@ -397,8 +399,8 @@ def ours_arm(args):
     launches_all = tot.item()
 
     extras = []
-    if n_gpus == 1 and not args.no_extra:
-        extras = extra_workloads(args, h, S, l2_flush)
+    if not args.no_extra:
+        extras = extra_workloads(args, h, S, l2_flush, rank, world)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -454,11 +456,14 @@ def ours_arm(args):
         dist.destroy_process_group()
 
 
-def extra_workloads(args, h, S, l2_flush):
-    """C2 and a C5 target slab on one GPU: value (matrix resident), roofline, and a small CPU sample each."""
+def extra_workloads(args, h, S, l2_flush, rank=0, world=1):
+    """C2 (one GPU only: BASELINE names it a 1-GPU config) and a C5 target slab (every GPU count, jobs sharded like the main
+    workload): value (matrix resident), roofline, and on one GPU a small CPU sample each."""
     import pandas as pd
     import torch
+    import torch.distributed as dist
     import recipes
+    from scribe_py_b200 import distributed as D
     peaks, peak_src = measured_peaks()
     out = []
     steps = max(2, min(args.steps, 5))
@@ -468,15 +473,32 @@ def extra_workloads(args, h, S, l2_flush):
         for _ in range(2):
             fn()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(); ev0.record()
         for _ in range(n_steps):
             l2_flush()
             vals = fn()
             add_stats(acc, h.stats())
-        ev1.record(); torch.cuda.synchronize()
-        return vals, ev0.elapsed_time(ev1) / n_steps, acc
+        ev1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / n_steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        return vals, ms, acc
 
     cores = os.cpu_count() or 1
+    if world == 1:
+        out.append(extra_c2(args, h, S, timed, steps, peaks, peak_src, cores))
+    out.append(extra_c5(args, h, S, D, timed, peaks, peak_src, cores, rank, world))
+    return out if rank == 0 else []
+
+
+def extra_c2(args, h, S, timed, steps, peaks, peak_src, cores):
+    import pandas as pd
+    import recipes
     # ---- C2: RDI all ordered pairs, 100 genes x 2000 cells, delays {1,5,10}
     G, T = 100, 2000
     E = recipes.rdi_synthetic(G, T, 2)
@@ -511,10 +533,14 @@ def extra_workloads(args, h, S, l2_flush):
         rec["cpu_baseline"] = {"value": len(sample) / dt, "unit": "evals/s", "cores": cores, "kind": cpu_kind(),
                                "sample": "%d seeded jobs, %.1f s" % (len(sample), dt),
                                "parity_max_abs_diff_on_sample": float(np.abs(np.array(cpu) - gpu).max())}
-    out.append(rec)
+    return rec
 
-    # ---- C5 target slab: uniformised RDI (cumi, KDE bw = 0.01), 1000 genes x 20 000 cells, all sources -> 4 targets, 3 delays
-    G, T, NT = 1000, 20000, 4
+
+def extra_c5(args, h, S, D, timed, peaks, peak_src, cores, rank, world):
+    # ---- C5 target slab: uniformised RDI (cumi, KDE bw = 0.01), 1000 genes x 20 000 cells, all sources -> 8 targets, 3 delays;
+    # the same 23 976 jobs at every GPU count, sharded across the ranks (strong scaling)
+    import recipes
+    G, T, NT = 1000, 20000, 8
     E = recipes.zscore_rows(recipes.ar_panel(G, T, 5))
     h.upload_matrix(E)
     src = np.concatenate([np.delete(np.arange(G, dtype=np.int32), t) for t in range(NT)])
@@ -524,14 +550,18 @@ def extra_workloads(args, h, S, l2_flush):
         sl = slice(i * len(src), (i + 1) * len(src))
         jobs["src"][sl] = src; jobs["dst"][sl] = dst; jobs["delay"][sl] = d
     opts = S._lib.make_opts(S._lib.EST_CUMI, 5)
-    vals, ms, acc = timed(lambda: h.lagged_jobs(jobs, opts), 2)
+
+    def evaluate(lo, hi, out_dev_ptr=None):
+        return h.lagged_jobs(jobs[lo:hi], opts, out_dev_ptr=out_dev_ptr)
+
+    vals, ms, acc = timed(lambda: D.sharded_evaluate(len(jobs), evaluate, h), 2)
     rec = {"workload": "target slab of the uniformised-RDI scale sweep (BASELINE configs[4]): cumi (KDE bw=0.01), 1,000 genes x 20,000 cells, "
-                       "all 999 sources -> %d targets x delays {1,5,10}; the full sweep is 250 such slabs" % NT,
-           "jobs_per_step": len(jobs), "value": len(jobs) / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "steps": 2,
+                       "all 999 sources -> %d targets x delays {1,5,10}, sharded over %d GPU(s); the full sweep is 125 such slabs" % (NT, world),
+           "jobs_per_step": len(jobs), "value": len(jobs) / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "steps": 2, "n_gpus": world,
            "full_config_extrapolated_s": 2997000 / (len(jobs) / (ms * 1e-3)),
            "roofline": roofline_of(acc, 2, "ksg_sweepw_kernel<1,6,2,true> + kde_sweep_kernel<2,2>", h.sm_count, peaks, peak_src, weighted=True,
                                    step_ms=ms, traffic=ncu_traffic("c5:ksg_sweepw_kernel<1,6,2,true>"))}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         # the reference's cumi at N = 20 000 takes ~10 s alone and far longer when every core runs one (memory-bound kd-tree
         # KDE): a handful of jobs keeps this leg bounded
         sample = [(int(src[i]), int(dst[i]), 1) for i in np.random.default_rng(1).choice(len(src), min(cores, 4), replace=False)]
@@ -546,8 +576,7 @@ def extra_workloads(args, h, S, l2_flush):
         rec["cpu_baseline"] = {"value": len(sample) / dt, "unit": "evals/s", "cores": cores, "kind": cpu_kind(),
                                "sample": "%d seeded cumi jobs at N = 19 999, %.1f s" % (len(sample), dt),
                                "parity_max_abs_diff_on_sample": float(np.abs(np.array(cpu) - gpu).max())}
-    out.append(rec)
-    return out
+    return rec
 
 
 def _json_only_stdout():

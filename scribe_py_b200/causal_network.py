@@ -169,9 +169,9 @@ class causal_model(object):
         it first if necessary) when that reproduces pandas bit for bit on probe rows; otherwise in pandas."""
         if self._normalize_on_device():
             return
-        cur = self.expression
-        e = cur.sub(cur.mean(axis=1), axis=0)
-        e = e.div(cur.std(axis=1), axis=0)
+        e = self.expression
+        e = e.sub(e.mean(axis=1), axis=0)
+        e = e.div(e.std(axis=1), axis=0)                          # std of the centred frame, as the reference's two statements do
         self.expression = e.fillna(0)
 
     # ------------------------------------------------------------------ device-side preprocessing
@@ -207,7 +207,8 @@ class causal_model(object):
             # pandas on a frame of the probe rows (several rows on purpose: the summation order of DataFrame.mean(axis=1)
             # depends on the frame's memory layout, and a one-row frame is laid out differently from a many-row one)
             f = pd.DataFrame(rows[:, run_off[r]:run_off[r + 1]].copy())
-            z = f.sub(f.mean(axis=1), axis=0).div(f.std(axis=1), axis=0).fillna(0).to_numpy()
+            c = f.sub(f.mean(axis=1), axis=0)
+            z = c.div(c.std(axis=1), axis=0).fillna(0).to_numpy()
             for i in range(len(probe)):
                 want.append((rows[i, run_off[r]:run_off[r + 1]], z[i]))
         pick = None
@@ -216,11 +217,11 @@ class causal_model(object):
                 ok = True
                 for seg, z in want:
                     n = len(seg)
-                    mean = self._ordered_sum(seg, mo) / n
-                    avg = self._ordered_sum(seg, ao) / n
+                    c = seg - self._ordered_sum(seg, mo) / n
+                    avg = self._ordered_sum(c, ao) / n
                     with np.errstate(invalid="ignore", divide="ignore"):
-                        sd = np.sqrt(np.add.reduce((avg - seg) * (avg - seg)) / (n - 1))
-                        got = (seg - mean) / sd
+                        sd = np.sqrt(np.add.reduce((avg - c) * (avg - c)) / (n - 1))
+                        got = c / sd
                     got[np.isnan(got)] = 0
                     if not np.array_equal(got, z):
                         ok = False

@@ -402,6 +402,9 @@ void run_jobs(scribe_handle* h, std::vector<JobDesc>& hj, int n_max, int dx, int
             const double scale = std::sqrt(1.4426950408889634 / (2.0 * o->bw * o->bw));
             if (ks) {
                 const int bps = (wpj + SWEEP_TPB / 32 - 1) / (SWEEP_TPB / 32);
+                job_absmax_kernel<<<(unsigned)nj, 128, 0, h->stream>>>(dj, D);      // bound of the KDE's FP32 box pre-filter
+                CU(cudaGetLastError());
+                h->st.kernel_launches++;
                 ks<<<(unsigned)(nj * bps), SWEEP_TPB, 0, h->stream>>>(dj, wpj, h->dims.as<int>(), scale, u, visited);
             } else {
                 kf<<<(unsigned)(nj * bpj_kde), TPB, 0, h->stream>>>(dj, bpj_kde, h->dims.as<int>(), scale, u);

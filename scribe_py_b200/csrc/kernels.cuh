@@ -1405,9 +1405,15 @@ ksg_strip2_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, c
     }
 }
 
-// Gaussian KDE inverse densities, sorted sweep: terms with (z_i - z_j)^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
-// than 2^-KDE_CUT (= 2^-44) each against a sum that is >= 1 (the self term), so a side is abandoned once the nearest unvisited
-// candidate is that far in the key coordinate for every query of the warp.
+// Gaussian KDE inverse densities, sorted sweep: terms with |P_i - P_j|^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
+// than 2^-KDE_CUT (= 2^-44) each against a sum that is >= 1 (the self term), so
+//   * a side of the sweep is abandoned once the nearest unvisited candidate is that far in the key coordinate for every
+//     query of the warp, and
+//   * inside the window only candidates that can be that close in EVERY density coordinate reach the exponential: the scan
+//     is an FP32 box pre-filter (|d_c| <= sqrt(KDE_CUT), bound widened by the FP32 rounding of the scaled coordinates; one
+//     packed subtract + one FSETP per coordinate), and the marked candidates -- ~6 % of the window at bw = 0.01 on z-scored
+//     data -- get the exact FP64 squared distance, F2F and MUFU.EX2.  ncu on the first form (every visited pair through the
+//     exponential) showed the XU pipe (F2F + MUFU) 86 % busy: the kernel was bound by conversions of negligible terms.
 constexpr double KDE_CUT = 44.0;     // N * 2^-44 < 2e-9 relative for N <= 2^15; the estimators' budget is 1e-5 absolute
 
 template <int DP, int Q>
@@ -1417,7 +1423,9 @@ kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int*
 {
     constexpr int W = SWEEP_TPB / 32;
     constexpr int KEY = DP - 1;                                   // dims[] lists the key column last
-    __shared__ __align__(16) double sbuf[W][DP][32];
+    constexpr int DPA = (DP + 1) & ~1;                            // float rows padded to whole pairs
+    __shared__ __align__(16) double sbuf[W][32][DPA];             // scaled candidates, FP64 (exact distance of marked candidates)
+    __shared__ __align__(16) float  sflt[W][32][DPA];             // the same in FP32 (box pre-filter)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int bpj = (warps_per_job + W - 1) / W;
     const int job = blockIdx.x / bpj;
@@ -1427,27 +1435,38 @@ kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int*
     const int w0 = wj * 32 * Q;
     if (wj >= warps_per_job || w0 >= n) return;
     const int c0 = w0 / 32, nchunks = (n + 31) / 32;
-    double (*buf)[32] = sbuf[wid];
+    double (*buf)[DPA] = sbuf[wid];
+    float  (*bfl)[DPA] = sflt[wid];
     const double* cp[DP];
     #pragma unroll
     for (int d = 0; d < DP; d++) cp[d] = jd.col[dims[d]];
     const double rcut = sqrt(KDE_CUT);                            // in scaled units
+    // FP32 bound of the box filter: the scaled FP64 coordinates are rounded to FP32 (<= 2^-24 relative each) and subtracted
+    // in FP32 (<= 2^-24 of the difference); absmax is the job's largest |raw coordinate| (job_absmax_kernel).  A non-finite
+    // bound (huge data) marks everything.
+    const float tcut = __double2float_ru(rcut * (1.0 + 0x1p-20) + fabs(jd.absmax * scale) * 0x1p-21 + 1e-30);
 
     auto load = [&](int chunk, double (&v)[DP]) {
         const int rank = chunk * 32 + lane;
         const bool ok = rank < n;
         const int idx = ok ? (jd.perm ? jd.perm[rank] : rank) : 0;
         #pragma unroll
-        for (int d = 0; d < DP; d++) v[d] = ok ? cp[d][idx] * scale : INFINITY;     // exp2(-inf) = 0
+        for (int d = 0; d < DP; d++) v[d] = ok ? cp[d][idx] * scale : INFINITY;     // never inside the box; exp2(-inf) = 0
     };
     auto stage = [&](const double (&v)[DP]) {
         __syncwarp();
         #pragma unroll
-        for (int d = 0; d < DP; d++) buf[d][lane] = v[d];
+        for (int d = 0; d < DPA; d += 2) {
+            double2 t; t.x = v[d]; t.y = (d + 1 < DP) ? v[d + 1 < DP ? d + 1 : d] : 0.0;
+            *reinterpret_cast<double2*>(&buf[lane][d]) = t;
+            float2 f; f.x = __double2float_rn(t.x); f.y = __double2float_rn(t.y);
+            *reinterpret_cast<float2*>(&bfl[lane][d]) = f;
+        }
         __syncwarp();
     };
 
     double qc[Q][DP]; int qidx[Q]; bool qok[Q];
+    unsigned long long qf2[Q][DPA / 2];
     #pragma unroll
     for (int q = 0; q < Q; q++) {
         const int rank = w0 + q * 32 + lane;
@@ -1456,24 +1475,68 @@ kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int*
         qidx[q] = jd.perm ? jd.perm[rr] : rr;
         #pragma unroll
         for (int d = 0; d < DP; d++) qc[q][d] = cp[d][qidx[q]] * scale;
+        #pragma unroll
+        for (int d = 0; d < DPA; d += 2) {
+            const float a = __double2float_rn(qc[q][d]), b = (d + 1 < DP) ? __double2float_rn(qc[q][d + 1 < DP ? d + 1 : d]) : 0.f;
+            asm("mov.b64 %0, {%1,%2};" : "=l"(qf2[q][d / 2]) : "f"(a), "f"(b));
+        }
     }
     double S[Q];
     #pragma unroll
     for (int q = 0; q < Q; q++) S[q] = 0.0;
 
     auto kde_chunk = [&]() {
+        unsigned mask[Q];
+        #pragma unroll
+        for (int q = 0; q < Q; q++) mask[q] = 0u;
+        #pragma unroll 1
+        for (int jb = 0; jb < 32; jb += 8) {
+            unsigned mb[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; q++) mb[q] = 0u;
+            #pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int j = jb + t;
+                unsigned long long cf2[DPA / 2];
+                if constexpr (DPA == 2) { cf2[0] = *reinterpret_cast<const unsigned long long*>(&bfl[j][0]); }
+                else { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&bfl[j][0]); cf2[0] = v.x; cf2[DPA / 2 - 1] = v.y; }
+                #pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    float df[DPA];
+                    #pragma unroll
+                    for (int d = 0; d < DPA; d += 2) {
+                        unsigned long long dd;
+                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(qf2[q][d / 2]), "l"(cf2[d / 2]));
+                        asm("mov.b64 {%0,%1}, %2;" : "=f"(df[d]), "=f"(df[d + 1]) : "l"(dd));
+                    }
+                    bool in = true;                                // unordered-or-less-equal: a NaN difference (inf - inf) stays marked
+                    #pragma unroll
+                    for (int d = 0; d < DP; d++) in = in && !(fabsf(df[d]) > tcut);
+                    mb[q] |= in ? (1u << t) : 0u;
+                }
+            }
+            #pragma unroll
+            for (int q = 0; q < Q; q++) mask[q] |= mb[q] << jb;
+        }
         float s32[Q];
         #pragma unroll
         for (int q = 0; q < Q; q++) s32[q] = 0.f;
-        #pragma unroll 4
-        for (int j = 0; j < 32; j++) {
+        unsigned any = 0u;
+        #pragma unroll
+        for (int q = 0; q < Q; q++) any |= mask[q];
+        while (any) {                                              // the next marked candidate of every slot per trip
+            any = 0u;
             #pragma unroll
             for (int q = 0; q < Q; q++) {
+                const bool has = mask[q] != 0u;
+                const int j = has ? __ffs(mask[q]) - 1 : 0;
+                mask[q] &= mask[q] - 1;
+                any |= mask[q];
                 double d2 = 0.0;
                 #pragma unroll
-                for (int d = 0; d < DP; d++) { const double df = qc[q][d] - buf[d][j]; d2 = fma(df, df, d2); }
+                for (int d = 0; d < DP; d++) { const double df = qc[q][d] - buf[j][d]; d2 = fma(df, df, d2); }
                 float e;
-                const float a = -(float)d2;
+                const float a = has ? -(float)d2 : -INFINITY;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
                 s32[q] += e;
             }

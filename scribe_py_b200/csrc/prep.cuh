@@ -112,8 +112,9 @@ coupling_normalise_kernel(double* __restrict__ S, double* __restrict__ V, int64_
 // (v - mean) / std(ddof = 1), NaN -> 0.  pandas forms the two statistics with different summation orders depending on its
 // version and the frame's memory layout, so both orders are implemented (0 = numpy pairwise, 1 = sequential) and the host
 // picks the pair that reproduces pandas on a few probe rows (and falls back to pandas itself when none does).
-//   mean        = sum_{order m}(v) / n
-//   avg         = sum_{order a}(v) / n ;  std = sqrt( sum_{pairwise}((avg - v)^2) / (n - 1) )      (pandas nanops.nanvar)
+//   c   = v - sum_{order m}(v) / n                                  (first statement of the reference: expression.sub(mean))
+//   avg = sum_{order a}(c) / n ;  std = sqrt( sum_{pairwise}((avg - c)^2) / (n - 1) )   (second statement: the std is taken of the
+//   z   = c / std                                                    ALREADY CENTRED frame; pandas nanops.nanvar)
 // One thread per (gene, run) segment: the sums are sequential by definition.
 // ------------------------------------------------------------------------------------------------
 __device__ inline double ordered_sum(const double* a, int64_t n, int order)
@@ -135,10 +136,11 @@ __global__ void normalize_rows_kernel(double* __restrict__ E, int64_t n_genes, i
     double* v = E + g * n_cells + run_off[r];
     double* sq = scratch + g * n_cells + run_off[r];
     const double mean = ordered_sum(v, n, mean_order) / (double)n;
+    for (int64_t i = 0; i < n; i++) v[i] = v[i] - mean;
     const double avg = ordered_sum(v, n, avg_order) / (double)n;
     for (int64_t i = 0; i < n; i++) { const double d = avg - v[i]; sq[i] = d * d; }
     const double sd = sqrt(np_pairwise_sum(sq, n) / (double)(n - 1));
-    for (int64_t i = 0; i < n; i++) { const double z = (v[i] - mean) / sd; v[i] = (z != z) ? 0.0 : z; }
+    for (int64_t i = 0; i < n; i++) { const double z = v[i] / sd; v[i] = (z != z) ? 0.0 : z; }
 }
 
 // causal_model.smooth (causal_network.py:97-101): rolling mean of `w` cells along every (gene, run) row, pandas' online

@@ -693,7 +693,8 @@ def test_normalize_smooth_on_device(S, golden_configs):
     # larger panel: every row against pandas, then rdi on the resident normalised matrix == rdi on the pandas-normalised frame
     E = recipes.ar_panel(40, 3000, 11)[:12]
     frame = pd.DataFrame(E, index=pd.Index(["g%02d" % i for i in range(12)], name="GENE_ID"))
-    want = frame.sub(frame.mean(axis=1), axis=0).div(frame.std(axis=1), axis=0).fillna(0)
+    want = frame.sub(frame.mean(axis=1), axis=0)
+    want = want.div(want.std(axis=1), axis=0).fillna(0)
     m = S.causal_model(frame)
     m.normalize()
     assert m._expr_stale

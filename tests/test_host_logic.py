@@ -124,6 +124,24 @@ def test_matrix_stays_resident_between_calls(S):
     assert np.allclose(m.expression.to_numpy().mean(axis=1), 0, atol=1e-12)
 
 
+def test_normalize_smooth_host_path_against_reference(S, golden_configs):
+    """the pandas paths of normalize()/smooth() (taken with the test double, and on the GPU for NaN-padded frames)"""
+    g = golden_configs
+    names = ["g%d" % i for i in range(6)]
+    m = S.causal_model(pd.DataFrame(g["norm_in"], index=pd.Index(names, name="GENE_ID")))
+    m.normalize()
+    assert np.array_equal(m.expression.to_numpy(dtype=float), g["norm_out"])
+    for w in (3, 7):
+        m = S.causal_model(pd.DataFrame(g["norm_in"], index=pd.Index(names, name="GENE_ID")))
+        m.smooth(w)
+        assert np.array_equal(m.expression.to_numpy(dtype=float), g["smooth%d_out" % w])
+        assert np.array_equal(np.asarray(m.expression.columns, dtype=np.int64), g["smooth%d_cols" % w])
+    runs, g6, _ = recipes.gv_e()
+    mm = S.causal_model(recipes.multi_run_frame(runs, g6))
+    mm.normalize()
+    assert np.array_equal(mm.expression.to_numpy(dtype=float), g["norm_multi_out"], equal_nan=True)
+
+
 def test_slab_partition():
     from scribe_py_b200.distributed import slab
     for n in (0, 1, 7, 8, 29700, 249500):
