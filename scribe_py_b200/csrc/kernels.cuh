@@ -1405,6 +1405,30 @@ ksg_strip2_kernel(const JobDesc* __restrict__ jobs, int strips_per_job, int k, c
     }
 }
 
+// FP32 box test of the KDE pre-filter: set `bit` unless some coordinate difference is certainly above T (chained unordered
+// compares and one predicated OR: DP + 1 issue slots)
+template <int NP>
+__device__ __forceinline__ void box_mark32(const float (&df)[NP], float T, unsigned bit, unsigned& mask)
+{
+    static_assert(NP >= 1 && NP <= 4, "1..4 density coordinates on the sweep");
+    if (NP == 1)
+        asm("{\n .reg .pred p;\n .reg .f32 a0;\n abs.f32 a0,%1;\n setp.leu.f32 p, a0, %2;\n @p or.b32 %0,%0,%3;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(T), "r"(bit));
+    else if (NP == 2)
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1;\n abs.f32 a0,%1; abs.f32 a1,%2;\n"
+            " setp.leu.f32 p, a0, %3;\n setp.leu.and.f32 p, a1, %3, p;\n @p or.b32 %0,%0,%4;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(T), "r"(bit));
+    else if (NP == 3)
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1,a2;\n abs.f32 a0,%1; abs.f32 a1,%2; abs.f32 a2,%3;\n"
+            " setp.leu.f32 p, a0, %4;\n setp.leu.and.f32 p, a1, %4, p;\n setp.leu.and.f32 p, a2, %4, p;\n @p or.b32 %0,%0,%5;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(df[NP > 2 ? 2 : 0]), "f"(T), "r"(bit));
+    else
+        asm("{\n .reg .pred p;\n .reg .f32 a0,a1,a2,a3;\n abs.f32 a0,%1; abs.f32 a1,%2; abs.f32 a2,%3; abs.f32 a3,%4;\n"
+            " setp.leu.f32 p, a0, %5;\n setp.leu.and.f32 p, a1, %5, p;\n setp.leu.and.f32 p, a2, %5, p;\n setp.leu.and.f32 p, a3, %5, p;\n"
+            " @p or.b32 %0,%0,%6;\n}"
+            : "+r"(mask) : "f"(df[0]), "f"(df[1]), "f"(df[NP > 2 ? 2 : 0]), "f"(df[NP > 3 ? 3 : 0]), "f"(T), "r"(bit));
+}
+
 // Gaussian KDE inverse densities, sorted sweep: terms with |P_i - P_j|^2 * log2(e)/(2 bw^2) > KDE_CUT contribute less
 // than 2^-KDE_CUT (= 2^-44) each against a sum that is >= 1 (the self term), so
 //   * a side of the sweep is abandoned once the nearest unvisited candidate is that far in the key coordinate for every
@@ -1509,10 +1533,10 @@ kde_sweep_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, const int*
                         asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(qf2[q][d / 2]), "l"(cf2[d / 2]));
                         asm("mov.b64 {%0,%1}, %2;" : "=f"(df[d]), "=f"(df[d + 1]) : "l"(dd));
                     }
-                    bool in = true;                                // unordered-or-less-equal: a NaN difference (inf - inf) stays marked
+                    float dn[DP];
                     #pragma unroll
-                    for (int d = 0; d < DP; d++) in = in && !(fabsf(df[d]) > tcut);
-                    mb[q] |= in ? (1u << t) : 0u;
+                    for (int d = 0; d < DP; d++) dn[d] = df[d];
+                    box_mark32<DP>(dn, tcut, 1u << t, mb[q]);      // unordered-or-less-equal: a NaN difference stays marked
                 }
             }
             #pragma unroll

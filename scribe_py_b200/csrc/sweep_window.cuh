@@ -27,7 +27,10 @@
 namespace scribe {
 
 #ifndef SWEEPW_UNROLL
-#define SWEEPW_UNROLL 8
+#define SWEEPW_UNROLL 16                  // candidates per scan block, unweighted kernels.  Measured on B200 (r2, tools/ab.py) 16 vs 8:
+#endif                                    // C2 -2.5 %, C3 -3.7 %, C4 -3.0 %, cmi at N = 20 000 -3.6 %; the weighted (cumi) kernels lose 9 %
+#ifndef SWEEPW_UNROLL_W                   // with 16 (code size), so they keep 8
+#define SWEEPW_UNROLL_W 8
 #endif
 #ifndef SWEEPW_MERGED
 #define SWEEPW_MERGED 0                   // 1: one marked-candidate loop for all query slots of a lane.  Measured on B200 (r2): +1..3 % time, off
@@ -201,7 +204,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     constexpr int NP  = D - 1;                    // non-key coordinates: x, y, z_0 .. z_{DZ-2}
     constexpr int NPA = (NP + 1) & ~1;            // padded to a multiple of 2 -> 16-byte rows of doubles, 8/16-byte rows of floats
     constexpr int W   = SWEEP_TPB / 32;
-    constexpr int UNR = SWEEPW_UNROLL;
+    constexpr int UNR = WEIGHTED ? SWEEPW_UNROLL_W : SWEEPW_UNROLL;
     constexpr int KL  = KCAP - 1;                 // list length: the k nearest OTHER points (the query itself is never inserted)
     __shared__ __align__(16) double sd[W][32][NPA];          // candidates, non-key coordinates (FP64)
     __shared__ __align__(16) float  sf[W][32][NPA];          // the same rounded to FP32 (pass 1 pre-filter)
