@@ -56,7 +56,7 @@ def measured_peaks():
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic_r2.json), or None."""
-    for name in ("traffic_r2.json", "traffic_r1.json"):
+    for name in ("traffic_r2.json", "r1/traffic_r1.json"):
         try:
             v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
             if v is not None:
@@ -251,29 +251,33 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-def roofline_of(st_sum, n_launch_calls, kernel, sm_count, peaks, peak_src, weighted=False, step_ms=None, traffic=None):
-    """ALU roofline of the estimator kernels from the library's per-call counters, summed over `n_launch_calls` calls."""
+def roofline_of(st_sum, n_steps, kernel, sm_count, peaks, peak_src, weighted=False, step_ms=None, traffic=None):
+    """ALU roofline of the estimator kernel, PER LAUNCH, from the library's per-call counters summed over `n_steps` steps
+    (a step of the coupling workload is several launches: the pair list is evaluated in chunks bounded by workspace)."""
     sm_clock_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
     alu_peak = sm_count * 128 * sm_clock_hz
-    k_ms = st_sum["estimator_ms"] / max(n_launch_calls, 1)
-    vk, vc, vd = (st_sum[k] / max(n_launch_calls, 1) for k in ("visited_knn", "visited_count", "visited_kde"))
-    pairs = st_sum["point_pairs"] / max(n_launch_calls, 1)
+    n_launch = max(int(st_sum.get("estimator_launches", 0)), 1)
+    if weighted:
+        n_launch = max(n_launch // 2, 1)                         # the KDE sweep and the estimator sweep count as one pair of launches
+    k_ms = st_sum["estimator_ms"] / n_launch
+    vk, vc, vd = (st_sum[k] / n_launch for k in ("visited_knn", "visited_count", "visited_kde"))
+    pairs = st_sum["point_pairs"] / n_launch
     ops = 6.0 * vk + 10.0 * vc + (6.0 * vd if weighted else 0.0)
     achieved = ops / (k_ms * 1e-3)
     dense = (22.0 if weighted else 16.0) * pairs / (k_ms * 1e-3)
     r = {"bound": "alu", "achieved": achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s", "frac": achieved / alu_peak,
-         "traffic": traffic, "kernel": kernel, "kernel_ms": k_ms,
+         "traffic": traffic, "kernel": kernel, "kernel_ms": k_ms, "launches_per_step": n_launch / max(n_steps, 1),
          "algorithmic_ops": "6 per kNN-pass visit + 10 per count-pass visit" + (" + 6 per KDE visit" if weighted else "")
                             + " (SURVEY 8d, D = 3), counted on the point pairs the sorted sweep visits",
-         "visits_per_step": {"knn": vk, "count": vc, "kde": vd, "dense_pairs_N2": pairs,
-                             "visited_fraction": (vk + vc) / max(2.0 * pairs, 1.0)},
+         "visits_per_launch": {"knn": vk, "count": vc, "kde": vd, "dense_pairs_N2": pairs,
+                               "visited_fraction": (vk + vc) / max(2.0 * pairs, 1.0)},
          "dense_equivalent": {"value": dense / 1e12, "frac_of_peak": dense / alu_peak,
                               "note": "%d x N^2 per job / kernel time: what a dense brute force would have to sustain for the same "
                                       "evals/s -- a speed-up figure, not a utilisation" % (22 if weighted else 16)},
          "peak_source": "SMs x 128 FP32 lanes x sm_max_mhz from MEASURED_PEAKS.json (%s); FADD issue rate confirmed 3.89/4 "
                         "warp-inst/clk/SM by tools/microbench.cu" % peak_src}
     if step_ms:
-        r["kernel_share_of_step"] = k_ms / step_ms
+        r["kernel_share_of_step"] = st_sum["estimator_ms"] / max(n_steps, 1) / step_ms
     return r
 
 
@@ -412,7 +416,7 @@ def ours_arm(args):
         jobs_rank = n_jobs / world
         n_eff = (acc["point_pairs"] / args.steps / max(jobs_rank, 1)) ** 0.5          # rms cells kept per pair on this rank
         algo_bytes = jobs_rank * (28.0 * C3_CELLS + 48.0 * n_eff)
-        roof["hbm"] = {"achieved_gbs": algo_bytes / (roof["kernel_ms"] * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+        roof["hbm"] = {"achieved_gbs": algo_bytes / (acc["estimator_ms"] / args.steps * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                        "note": "non-binding: per pair 3 columns + the sort order read (28 B x cells), 3 compacted columns written and "
                                "read once (48 B x cells kept, rms %.0f)" % n_eff}
         line = {
