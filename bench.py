@@ -497,7 +497,32 @@ def extra_workloads(args, h, S, l2_flush, rank=0, world=1):
     if world == 1:
         out.append(extra_c2(args, h, S, timed, steps, peaks, peak_src, cores))
     out.append(extra_c5(args, h, S, D, timed, peaks, peak_src, cores, rank, world))
+    if world == 1:
+        out.append(extra_umi_knn(h, S))
     return out if rank == 0 else []
+
+
+def extra_umi_knn(h, S):
+    """estimator-level umi (Euclidean sweep vs the generic thread-per-query kernel) and the 625-query kNN grid regressor"""
+    import recipes
+    E = recipes.zscore_rows(recipes.ar_panel(16, 20000, 5))
+    x, y = E[0, :-1, None], E[1, 1:, None]
+    rec = {"workload": "umi(x, y) at N = 19 999 (information_estimators.py:209-277) and viz_causality's kNN grid regressor "
+                       "(625 queries, plot/heatmaps.py:405-423) on one gene pair", "unit": "ms per call (host arrays in, value out)"}
+    for path, key in ((S._lib.PATH_SWEEP, "umi_sweep_ms"), (S._lib.PATH_GENERIC, "umi_generic_ms")):
+        opts = S._lib.make_opts(S._lib.EST_UMI, 5, "kde", 5, 0.01, path=path)
+        v = h.estimate(x, y, None, opts)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            v = h.estimate(x, y, None, opts)
+        rec[key] = (time.perf_counter() - t0) / 3 * 1e3
+        rec[key.replace("_ms", "_value")] = v
+    S.heatmaps.causality_grid(E[0], E[1])
+    t0 = time.perf_counter()
+    for _ in range(10):
+        S.heatmaps.causality_grid(E[0], E[1])
+    rec["knn_grid_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+    return rec
 
 
 def extra_c2(args, h, S, timed, steps, peaks, peak_src, cores):

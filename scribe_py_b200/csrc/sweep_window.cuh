@@ -35,6 +35,9 @@ namespace scribe {
 #ifndef SWEEPW_MERGED
 #define SWEEPW_MERGED 0                   // 1: one marked-candidate loop for all query slots of a lane.  Measured on B200 (r2): +1..3 % time, off
 #endif
+#ifndef SWEEPW_FINE_ALL
+#define SWEEPW_FINE_ALL 0                 // 1: insert marked candidates after every scan block in every chunk, not only in the centre chunks
+#endif
 #ifndef SWEEPW_RANK
 #define SWEEPW_RANK 0                     // 1: pass 2 tests integer rank windows on the FP32/ALU pipes instead of FP64 differences (bit-identical;
                                           // measured on B200, r2: +4 % time at N = 2000, -1.5 % on cumi at N = 20 000 -- see DESIGN.md)
@@ -373,7 +376,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         }
     };
     auto knn_chunk = [&](bool all) {
-        if (all) knn_body(std::integral_constant<int, 0>{}, -1, false); else knn_body(std::integral_constant<int, Q - 1>{}, -1, false);
+        if (all) knn_body(std::integral_constant<int, 0>{}, -1, SWEEPW_FINE_ALL != 0); else knn_body(std::integral_constant<int, Q - 1>{}, -1, SWEEPW_FINE_ALL != 0);
     };
     auto set_qf = [&]() {
         #pragma unroll

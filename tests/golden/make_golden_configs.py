@@ -208,7 +208,54 @@ def part_post(procs):
         w = u / np.sum(u)
         exp_y[i] = sum(np.array(w) * np.array(subset_dat))
     out["knnreg_query"] = xz_query; out["knnreg_raw"] = exp_y.copy(); out["knnreg_norm"] = exp_y / max(exp_y)
+    out.update(part_load_anndata())
     return out
+
+
+def load_anndata_case():
+    """AnnData stand-in with three dpt_groups branches (one of a single cell, which the reference skips), shuffled cells"""
+    rng = np.random.default_rng(8)
+    G, n = 4, 90
+    X = rng.standard_normal((n, G)).cumsum(axis=0) * 0.3 + rng.standard_normal((n, G))
+    branch = np.array(["1"] * 50 + ["2"] * 39 + ["3"])
+    perm = rng.permutation(n)
+    X, branch = X[perm], branch[perm]
+    ptime = rng.random(n)
+    obs = pd.DataFrame({"dpt_groups": branch, "dpt_pseudotime": ptime}, index=["c%d" % i for i in range(n)])
+    genes = ["A", "B", "C", "D"]
+    return recipes.FakeAnnData({"spliced": X.copy()}, genes, obs_names=list(obs.index), X=X, obs=obs), genes
+
+
+def part_load_anndata():
+    """Scribe.read_export.load_anndata (read_export.py:16-98) run from a /tmp copy whose ONLY change is `np.where(...)` ->
+    `np.where(...)[0]` at :56 (pandas >= 2 rejects the tuple as a column indexer)."""
+    import importlib, shutil, tempfile, types
+    src = open("/root/reference/Scribe/read_export.py").read()
+    old = "cur_id = np.where(np.array(keys) == str(key))"
+    assert src.count(old) == 1
+    tmp = tempfile.mkdtemp(prefix="scribe_ref_re_")
+    open(os.path.join(tmp, "read_export.py"), "w").write(src.replace(old, old + "[0]"))
+    for f in ("causal_network.py", "information_estimators.py", "logging.py", "settings.py"):
+        os.symlink(os.path.join("/root/reference/Scribe", f), os.path.join(tmp, f))
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    saved = {k: v for k, v in sys.modules.items() if k == "Scribe" or k.startswith("Scribe.")}
+    for k in saved:
+        del sys.modules[k]
+    pkg = types.ModuleType("Scribe"); pkg.__path__ = [tmp]; sys.modules["Scribe"] = pkg
+    try:
+        re_ = importlib.import_module("Scribe.read_export")
+        ad, genes = load_anndata_case()
+        m = re_.load_anndata(ad)
+    finally:
+        for k in [k for k in sys.modules if k == "Scribe" or k.startswith("Scribe.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        shutil.rmtree(tmp)
+    e = m.expression
+    return {"loadann_expression": e.to_numpy(dtype=float),
+            "loadann_index_gene": np.array([str(t[0]) for t in e.index]), "loadann_index_run": np.array([str(t[1]) for t in e.index]),
+            "loadann_node_ids": np.array([str(v) for v in m.node_ids]), "loadann_run_ids": np.array([str(v) for v in m.run_ids])}
 
 
 def part_diffcrdi(procs):

@@ -142,6 +142,19 @@ def test_normalize_smooth_host_path_against_reference(S, golden_configs):
     assert np.array_equal(mm.expression.to_numpy(dtype=float), g["norm_multi_out"], equal_nan=True)
 
 
+def test_load_anndata_against_reference(S, golden_configs):
+    """load_anndata against the reference's own read_export.load_anndata (one-token pandas fix, see make_golden_configs.py):
+    same rows, same (gene, run) order, same pseudotime ordering of every branch, same NaN padding"""
+    import make_golden_configs as mg
+    ad, genes = mg.load_anndata_case()
+    m = S.load_anndata(ad)
+    g = golden_configs
+    e = m.expression
+    assert [str(t[0]) for t in e.index] == list(g["loadann_index_gene"]) and [str(t[1]) for t in e.index] == list(g["loadann_index_run"])
+    assert np.array_equal(e.to_numpy(dtype=float), g["loadann_expression"], equal_nan=True)
+    assert [str(v) for v in m.node_ids] == list(g["loadann_node_ids"]) and [str(v) for v in m.run_ids] == list(g["loadann_run_ids"])
+
+
 def test_slab_partition():
     from scribe_py_b200.distributed import slab
     for n in (0, 1, 7, 8, 29700, 249500):
