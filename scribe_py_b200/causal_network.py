@@ -301,7 +301,7 @@ class causal_model(object):
             for g_i, g in enumerate(lay["node_ids"]):
                 for r_i, run in enumerate(lay["runs"]):
                     rows[pos[(g, run)], :ro[r_i + 1] - ro[r_i]] = E[g_i, ro[r_i]:ro[r_i + 1]]
-            frame = pd.DataFrame(rows, index=lay["index"])
+            frame = pd.DataFrame(rows, index=lay["index_obj"])
         self._expr = frame
         self._expr_stale = False
 
@@ -331,7 +331,8 @@ class causal_model(object):
             columns = [list(range(int(run_off[r + 1] - run_off[r]))) for r in range(len(runs))]
         self._dev = None if token is None else {
             "token": token, "fingerprint": self._fingerprint(expr), "node_ids": node_ids, "run_off": np.asarray(run_off, dtype=np.int64),
-            "runs": runs, "padded": padded, "index": expr.index if runs == [None] else list(expr.index), "columns": columns,
+            "runs": runs, "padded": padded, "index": expr.index if runs == [None] else list(expr.index), "index_obj": expr.index,
+            "columns": columns,
             "n_cells": int(E.shape[1]), "E_host": None}
         if runs == [None] and not (len(expr.index) == len(node_ids) and list(expr.index) == node_ids):
             self._dev = None                                   # reordered / subset rows: no write-back layout, upload every time

@@ -733,6 +733,35 @@ def test_umi_sweep_against_oracle_and_generic(S, k, density):
                 assert abs(h.estimate(x, y, None, opts) - ref) <= TOL_KDE, (n, path)
 
 
+def test_post_processing_edge_cases(S):
+    """NaN entries, degenerate sizes and empty results of the device post-processing entry points"""
+    from fake_device import FakeHandle
+    h, f = S._lib.default_handle(), FakeHandle()
+    rng = np.random.default_rng(12)
+    M = rng.random((7, 7)); M[2, 3] = np.nan; M[5, 5] = np.nan
+    with np.errstate(invalid="ignore"):
+        want = f.clr(M, True)
+    assert np.allclose(h.clr(M, True), want, atol=1e-12, rtol=0, equal_nan=True)
+    one = np.array([[0.3, 0.7]])                                  # one row: the column std (ddof = 1) is NaN, the row std is not
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert np.allclose(h.clr(one, True), f.clr(one, True), equal_nan=True, atol=1e-12, rtol=0)
+    a, b, w = h.top_edges(M, 1000)                                # more requested than exist: every kept entry, NaN dropped
+    fa, fb, fw = f.top_edges(M, 1000)
+    assert np.array_equal(a, fa) and np.array_equal(b, fb) and np.array_equal(w, fw) and len(w) < 49
+    a, b, w = h.top_edges(np.full((4, 4), np.nan), 5)
+    assert len(a) == 0 and len(w) == 0
+    scores = rng.random((6, 6)); scores[1, 4] = np.nan            # a NaN score is not ranked
+    truth = (rng.random((6, 6)) < 0.3).astype(np.uint8); truth[0, 1] = 1; truth[1, 0] = 0
+    au, x, y = h.roc(scores, truth)
+    i, j = np.nonzero(~np.eye(6, dtype=bool) & ~np.isnan(scores))
+    order = np.argsort(-scores[i, j], kind="stable"); hit = truth[i, j][order].astype(bool)
+    tp = np.concatenate(([0], np.cumsum(hit))); fp = np.concatenate(([0], np.cumsum(~hit)))
+    assert len(x) == len(tp) and np.array_equal(x, fp / fp[-1]) and np.array_equal(y, tp / tp[-1])
+    # kNN regressor with fewer data points than k + 1: missing neighbours are at infinity and carry no weight
+    out = h.knn_regress([0.0, 1.0, 2.0], [0.0, 0.0, 0.0], [5.0, 7.0, 9.0], [0.1], [0.0], k=5)
+    d = np.array([0.9, 1.9]); u = np.exp(-d / d.min()); assert abs(out[0] - (u / u.sum() * np.array([7.0, 9.0])).sum()) < 1e-12
+
+
 def test_knn_grid_regressor(S, golden_configs):
     """the 625-query kNN grid regressor of viz_causality (plot/heatmaps.py:389-428) against the reference's own scipy calls"""
     E = recipes.rdi_synthetic(6, 700, 9)
