@@ -138,7 +138,7 @@ def _coupling_plan(adata, TFs=None, Targets=None, t0_key='spliced', t1_key='velo
     ia = np.array([col[g] for g in TFs], dtype=np.int32)
     ib = np.array([col[g] for g in Targets], dtype=np.int32)
     bb, aa = np.meshgrid(np.arange(len(Targets)), np.arange(len(TFs)), indexing="ij")
-    names_differ = np.asarray(Targets, dtype=object)[:, None] != np.asarray(TFs, dtype=object)[None, :]     # skip g_a == g_b (Scribe.py:112)
+    names_differ = ib[:, None] != ia[None, :]        # skip g_a == g_b (Scribe.py:112); names are unique, so compare their positions
     aa, bb = aa[names_differ], bb[names_differ]
     return {"TFs": TFs, "Targets": Targets, "genes": genes, "aa": aa, "bb": bb, "src": np.ascontiguousarray(ia[aa]),
             "dst": np.ascontiguousarray(ib[bb]), "t0_key": t0_key, "t1_key": t1_key, "normalize": normalize}

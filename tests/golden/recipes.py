@@ -128,7 +128,8 @@ def coupling_panel(G, N, seed=3):
     par = rng.integers(0, G, (G, 2)); co = rng.uniform(-0.5, 0.5, (G, 2))
     vel = co[:, 0] * (spl[:, par[:, 0]] - spl[:, par[:, 0]].mean(0)) + co[:, 1] * (spl[:, par[:, 1]] - spl[:, par[:, 1]].mean(0)) \
         - 0.2 * spl + 0.1 * rng.standard_normal((N, G))
-    return spl, vel, ["g%04d" % i for i in range(G)]
+    # (fancy indexing leaves `vel` in a non-C memory order; an AnnData layer is a plain C-contiguous cells x genes array)
+    return np.ascontiguousarray(spl), np.ascontiguousarray(vel), ["g%04d" % i for i in range(G)]
 
 
 # gene subsets of the named configs on which the UNMODIFIED reference was run (tests/golden/make_golden_configs.py)
