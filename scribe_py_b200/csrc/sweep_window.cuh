@@ -35,6 +35,9 @@ namespace scribe {
 #ifndef SWEEPW_MERGED
 #define SWEEPW_MERGED 0                   // 1: one marked-candidate loop for all query slots of a lane.  Measured on B200 (r2): +1..3 % time, off
 #endif
+#ifndef SWEEPW_CPASYNC
+#define SWEEPW_CPASYNC 0                  // 1: pass 2 of unweighted jobs with pre-sorted columns (dynamics coupling) stages its candidate
+#endif                                    // chunks with cp.async into a double buffer instead of LDG -> registers -> STS (experiment, r2)
 #ifndef SWEEPW_FINE_ALL
 #define SWEEPW_FINE_ALL 0                 // 1: insert marked candidates after every scan block in every chunk, not only in the centre chunks
 #endif
@@ -210,6 +213,9 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     constexpr int UNR = WEIGHTED ? SWEEPW_UNROLL_W : SWEEPW_UNROLL;
     constexpr int KL  = KCAP - 1;                 // list length: the k nearest OTHER points (the query itself is never inserted)
     __shared__ __align__(16) double sd[W][32][NPA];          // candidates, non-key coordinates (FP64)
+#if SWEEPW_CPASYNC
+    __shared__ __align__(16) double sd2[WEIGHTED ? 1 : W][WEIGHTED ? 1 : 32][NPA];      // second buffer of the cp.async pipeline
+#endif
     __shared__ __align__(16) float  sf[W][32][NPA];          // the same rounded to FP32 (pass 1 pre-filter)
     __shared__ __align__(8)  double sk[W][32];               // candidates, key coordinate
     __shared__ __align__(8)  double sw[WEIGHTED ? W : 1][WEIGHTED ? 66 : 1];   // cumi: weights [0..31]; DZ == 1: their exclusive prefix sums at [32..64]
@@ -765,7 +771,44 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             else     count_body_rank(std::integral_constant<int, Q - 1>{}, c * 32);
             nvis2 += all ? Q : 1;
         }
-    } else {
+    }
+#if SWEEPW_CPASYNC
+    else if (!WEIGHTED && perm == nullptr) {
+        // cp.async pipeline: chunk c + 1 is copied global -> shared (8 bytes per lane and coordinate, no registers) while
+        // chunk c is scanned; lanes beyond n copy nothing (their slots keep stale data: never inside a key window)
+        double (*buf[2])[NPA] = { sd[wid], sd2[WEIGHTED ? 0 : wid] };
+        auto issue = [&](int c, double (*dst)[NPA]) {
+            const int rank = c * 32 + lane;
+            if (rank < n) {
+                #pragma unroll
+                for (int d = 0; d < NP; d++) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(&dst[lane][d]);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(jd.col[d] + rank));
+                }
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        __syncwarp();
+        issue(cmin, buf[0]);
+        int cur_b = 0;
+        for (int c = cmin; c <= cmax; c++) {
+            if (c < cmax) issue(c + 1, buf[cur_b ^ 1]); else asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 1;");
+            __syncwarp();
+            bd = buf[cur_b];
+            bool all = Q == 1;
+            #pragma unroll
+            for (int q = 0; q < Q - 1; q++) all |= (c >= clo[q]) & (c <= chi[q]);
+            if (all) count_body(std::integral_constant<int, 0>{}, c * 32);
+            else     count_body(std::integral_constant<int, Q - 1>{}, c * 32);
+            nvis2 += all ? Q : 1;
+            __syncwarp();
+            cur_b ^= 1;
+        }
+        asm volatile("cp.async.wait_group 0;");
+    }
+#endif
+    else {
         Chunk<D, WEIGHTED> nxt = load_chunk<D, WEIGHTED>(jd, cmin, lane, n), cur;
         for (int c = cmin; c <= cmax; c++) {
             cur = nxt;
