@@ -254,15 +254,21 @@ class causal_model(object):
         raw = self.expression_raw
         if not isinstance(raw, pd.DataFrame) or window < 1:
             return False
-        keep_expr, keep_stale, keep_dev = getattr(self, "_expr", None), self._expr_stale, self._dev
+        if getattr(self, "_expr_stale", False):
+            self._materialise_expression()                         # the current frame must survive a declined attempt
+        keep_expr, keep_dev = getattr(self, "_expr", None), self._dev
+        ok = False
         try:
-            self._expr, self._expr_stale, self._dev = raw, False, None
+            self._expr, self._expr_stale, self._dev = raw, False, None     # make the RAW matrix the resident one
             node_ids, run_off, _ = self._ensure_resident()
             lay = self._dev
-            if lay is None or lay["padded"] or min(np.diff(run_off)) < window:
-                raise AssertionError
+            ok = lay is not None and not lay["padded"] and min(np.diff(run_off)) >= window
         except AssertionError:
-            self._expr, self._expr_stale, self._dev = keep_expr, keep_stale, keep_dev
+            ok = False
+        finally:
+            if not ok:                                             # declined (or failed): the model is as it was, minus the device copy
+                self._expr, self._expr_stale, self._dev = keep_expr, False, None
+        if not ok:
             return False
         n_runs = len(run_off) - 1
         probe = self._probe_rows(len(node_ids))
@@ -274,7 +280,7 @@ class causal_model(object):
                 seg = before[g][run_off[r]:run_off[r + 1]]
                 want = pd.Series(seg).rolling(window=window).mean().to_numpy()[window - 1:]
                 if not np.array_equal(v[new_off[r]:new_off[r + 1]], want, equal_nan=True):
-                    self._expr, self._expr_stale, self._dev = keep_expr, keep_stale, None
+                    self._expr, self._expr_stale, self._dev = keep_expr, False, None
                     return False
         lay = dict(lay)
         lay["run_off"] = np.asarray(new_off, dtype=np.int64)

@@ -454,7 +454,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     {   // outward sweep: whichever side still has a candidate that some query needs (key distance below its k-th distance)
         int cl = c0 - 1, cr = c0 + Q;
         bool toggle = false;
-        Chunk<D, WEIGHTED> Lc, Rc, cur;
+        Chunk<D, WEIGHTED> Lc, Rc;
         if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n);
         if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n);
         auto need = [&](double znext) {
@@ -474,9 +474,18 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
             const bool left = al && (!ar || toggle);
             toggle = !toggle;
             const unsigned act = left ? al : ar;
-            if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
-            else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
-            stage(cur, true);
+            // stage straight from the prefetched registers, then reuse them for the next prefetch (issued before the scan, so
+            // its latency still hides behind it): no chunk-to-chunk register copies (they were ~5 % of the instructions)
+            // (measured, tools/ab.py r2: -1.5 % on C3, -0.8 % on C2; the weighted kernels lose 3.5 % with it and keep the copy)
+            if constexpr (WEIGHTED) {
+                Chunk<D, WEIGHTED> cur;
+                if (left) { cur = Lc; --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
+                else      { cur = Rc; ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
+                stage(cur, true);
+            } else {
+                if (left) { stage(Lc, true); --cl; if (cl >= 0) Lc = load_chunk<D, WEIGHTED>(jd, cl, lane, n); }
+                else      { stage(Rc, true); ++cr; if (cr < nchunks) Rc = load_chunk<D, WEIGHTED>(jd, cr, lane, n); }
+            }
             const bool all = (act & ((1u << (Q - 1)) - 1u)) != 0u || Q == 1;
             knn_chunk(all);
             nvis += all ? Q : 1;
@@ -809,11 +818,16 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     }
 #endif
     else {
-        Chunk<D, WEIGHTED> nxt = load_chunk<D, WEIGHTED>(jd, cmin, lane, n), cur;
+        Chunk<D, WEIGHTED> ch = load_chunk<D, WEIGHTED>(jd, cmin, lane, n);
         for (int c = cmin; c <= cmax; c++) {
-            cur = nxt;
-            if (c < cmax) nxt = load_chunk<D, WEIGHTED>(jd, c + 1, lane, n);
-            stage(cur, false);
+            if constexpr (WEIGHTED) {
+                const Chunk<D, WEIGHTED> cur = ch;
+                if (c < cmax) ch = load_chunk<D, WEIGHTED>(jd, c + 1, lane, n);
+                stage(cur, false);
+            } else {
+                stage(ch, false);
+                if (c < cmax) ch = load_chunk<D, WEIGHTED>(jd, c + 1, lane, n);
+            }
             bool all = Q == 1;
             #pragma unroll
             for (int q = 0; q < Q - 1; q++) all |= (c >= clo[q]) & (c <= chi[q]);
