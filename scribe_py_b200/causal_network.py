@@ -285,6 +285,7 @@ class causal_model(object):
         lay = dict(lay)
         lay["run_off"] = np.asarray(new_off, dtype=np.int64)
         lay["columns"] = [c[window - 1:] for c in lay["columns"]]
+        lay["frame_columns"] = lay["frame_columns"][window - 1:]
         lay["n_cells"] = int(new_off[-1])
         self._dev = lay
         self._expr_stale = True
@@ -307,7 +308,8 @@ class causal_model(object):
             for g_i, g in enumerate(lay["node_ids"]):
                 for r_i, run in enumerate(lay["runs"]):
                     rows[pos[(g, run)], :ro[r_i + 1] - ro[r_i]] = E[g_i, ro[r_i]:ro[r_i + 1]]
-            frame = pd.DataFrame(rows, index=lay["index_obj"])
+            labels = lay["frame_columns"]
+            frame = pd.DataFrame(rows, index=lay["index_obj"], columns=labels[:width] if len(labels) >= width else None)
         self._expr = frame
         self._expr_stale = False
 
@@ -338,6 +340,7 @@ class causal_model(object):
         self._dev = None if token is None else {
             "token": token, "fingerprint": self._fingerprint(expr), "node_ids": node_ids, "run_off": np.asarray(run_off, dtype=np.int64),
             "runs": runs, "padded": padded, "index": expr.index if runs == [None] else list(expr.index), "index_obj": expr.index,
+            "frame_columns": list(expr.columns),
             "columns": columns,
             "n_cells": int(E.shape[1]), "E_host": None}
         if runs == [None] and not (len(expr.index) == len(node_ids) and list(expr.index) == node_ids):

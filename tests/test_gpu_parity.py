@@ -762,6 +762,31 @@ def test_post_processing_edge_cases(S):
     d = np.array([0.9, 1.9]); u = np.exp(-d / d.min()); assert abs(out[0] - (u / u.sum() * np.array([7.0, 9.0])).sum()) < 1e-12
 
 
+def test_normalize_smooth_multi_run_equal_lengths(S):
+    """multi-run frames WITHOUT NaN padding (equal run lengths) also take the device path: every (gene, run) row is one
+    segment; the frame rebuilt from the device keeps the (GENE_ID, RUN_ID) index"""
+    rng = np.random.default_rng(21)
+    runs = [rng.gamma(2.0, 1.0, (5, 120)), rng.gamma(2.0, 1.0, (5, 120))]
+    genes = ["g%d" % i for i in range(5)]
+    df = recipes.multi_run_frame(runs, genes)
+    c = df.sub(df.mean(axis=1), axis=0)
+    want = c.div(c.std(axis=1), axis=0).fillna(0)
+    m = S.causal_model(df)
+    m.normalize()
+    assert m._expr_stale
+    got = m.expression
+    assert list(got.index) == list(df.index) and got.index.names == df.index.names
+    assert np.array_equal(got.to_numpy(dtype=float), want.to_numpy(dtype=float))
+    r = m.rdi([1, 2]); r2 = S.causal_model(want).rdi([1, 2])
+    for d in (1, 2):
+        assert np.array_equal(r[d].to_numpy(dtype=float), r2[d].to_numpy(dtype=float), equal_nan=True)
+    m = S.causal_model(df)
+    m.smooth(4)
+    sm = df.T.rolling(window=4).mean().T.dropna(axis=1, how="all")
+    assert np.array_equal(m.expression.to_numpy(dtype=float), sm.to_numpy(dtype=float))
+    assert list(m.expression.columns) == list(sm.columns) and list(m.expression.index) == list(sm.index)
+
+
 def test_knn_grid_regressor(S, golden_configs):
     """the 625-query kNN grid regressor of viz_causality (plot/heatmaps.py:389-428) against the reference's own scipy calls"""
     E = recipes.rdi_synthetic(6, 700, 9)
