@@ -35,6 +35,15 @@ namespace scribe {
 #ifndef SWEEPW_MERGED
 #define SWEEPW_MERGED 0                   // 1: one marked-candidate loop for all query slots of a lane.  Measured on B200 (r2): +1..3 % time, off
 #endif
+#ifndef SWEEPW_UNROLL_C
+#define SWEEPW_UNROLL_C SWEEPW_UNROLL
+#endif
+#ifndef SWEEPW_UNROLL_CW
+#define SWEEPW_UNROLL_CW SWEEPW_UNROLL_W
+#endif
+#ifndef SWEEPW_WFMA
+#define SWEEPW_WFMA 0                     // 1: weighted count pass accumulates W_yz with an indicator DFMA instead of a predicated DADD
+#endif
 #ifndef SWEEPW_CPASYNC
 #define SWEEPW_CPASYNC 0                  // 1: pass 2 of unweighted jobs with pre-sorted columns (dynamics coupling) stages its candidate
 #endif                                    // chunks with cp.async into a double buffer instead of LDG -> registers -> STS (experiment, r2)
@@ -114,9 +123,17 @@ __device__ __forceinline__ void ball_bit2(double d0, double d1, double e, unsign
 //   DZ  > 1: z-ball (extra conditioning columns) inside the window -> bz bit, W_z += w; then the y-ball inside it
 __device__ __forceinline__ void wball_y(double dy, double e, double w, unsigned win, unsigned bit, unsigned& by, double& wyz)
 {
+#if SWEEPW_WFMA
+    // W_yz += w * [inside] as one DFMA with a 0.0 / 1.0 indicator built from the predicate (SEL of the high word): ptxas turns
+    // a predicated add.f64 into DADD + 2 FSEL, this form is SEL + DFMA.  fma(w, 1, acc) == acc + w exactly.
+    asm("{\n .reg .pred pin,p;\n .reg .b32 t,hi;\n .reg .f64 a,ind;\n and.b32 t,%4,%5;\n setp.ne.u32 pin,t,0;\n abs.f64 a,%2;\n"
+        " setp.le.and.f64 p,a,%3,pin;\n selp.b32 hi,0x3ff00000,0,p;\n mov.b64 ind,{%7,hi};\n fma.rn.f64 %1,%6,ind,%1;\n @p or.b32 %0,%0,%5;\n}"
+        : "+r"(by), "+d"(wyz) : "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w), "r"(0));
+#else
     asm("{\n .reg .pred pin,p;\n .reg .b32 t;\n .reg .f64 a;\n and.b32 t,%4,%5;\n setp.ne.u32 pin,t,0;\n abs.f64 a,%2;\n"
         " setp.le.and.f64 p,a,%3,pin;\n @p add.f64 %1,%1,%6;\n @p or.b32 %0,%0,%5;\n}"
         : "+r"(by), "+d"(wyz) : "d"(dy), "d"(e), "r"(win), "r"(bit), "d"(w));
+#endif
 }
 __device__ __forceinline__ void wball_zy(double dz0, double dz1, bool two, double dy, double e, double w, unsigned win, unsigned bit,
                                          unsigned& bz, unsigned& by, double& wz, double& wyz)
@@ -211,6 +228,7 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     constexpr int NPA = (NP + 1) & ~1;            // padded to a multiple of 2 -> 16-byte rows of doubles, 8/16-byte rows of floats
     constexpr int W   = SWEEP_TPB / 32;
     constexpr int UNR = WEIGHTED ? SWEEPW_UNROLL_W : SWEEPW_UNROLL;
+    constexpr int UNRC = WEIGHTED ? SWEEPW_UNROLL_CW : SWEEPW_UNROLL_C;        // count-pass scan blocks
     constexpr int KL  = KCAP - 1;                 // list length: the k nearest OTHER points (the query itself is never inserted)
     __shared__ __align__(16) double sd[W][32][NPA];          // candidates, non-key coordinates (FP64)
 #if SWEEPW_CPASYNC
@@ -641,12 +659,12 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         #pragma unroll
         for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; zw[q] = range_mask(lo[q] - base, hi[q] - base); }
         #pragma unroll 1
-        for (int jb = 0; jb < 32; jb += UNR) {
+        for (int jb = 0; jb < 32; jb += UNRC) {
             unsigned bx[Q], by[Q], bz[Q], zb[Q];
             #pragma unroll
             for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; zb[q] = zw[q] >> jb; }
             #pragma unroll
-            for (int t = 0; t < UNR; t++) {
+            for (int t = 0; t < UNRC; t++) {
                 const int j = jb + t;
                 double cc[NPA];
                 #pragma unroll
@@ -686,12 +704,12 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         #pragma unroll
         for (int q = 0; q < Q; q++) { mx[q] = my[q] = 0u; mz[q] = 0u; zw[q] = range_mask(lo[q] - base, hi[q] - base); }
         #pragma unroll 1
-        for (int jb = 0; jb < 32; jb += UNR) {
+        for (int jb = 0; jb < 32; jb += UNRC) {
             unsigned bx[Q], by[Q], bz[Q], zb[Q];
             #pragma unroll
             for (int q = 0; q < Q; q++) { bx[q] = by[q] = 0u; bz[q] = 0u; zb[q] = zw[q] >> jb; }
             #pragma unroll
-            for (int t = 0; t < UNR; t++) {
+            for (int t = 0; t < UNRC; t++) {
                 const int j = jb + t;
                 unsigned long long cf2[NPA / 2];
                 if constexpr (NPA == 2) { cf2[0] = *reinterpret_cast<const unsigned long long*>(&bf[j][0]); }
