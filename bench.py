@@ -109,6 +109,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # workloads (synthetic, seeded; generators shared with the parity tests: tests/golden/recipes.py)
 # ----------------------------------------------------------------------------------------------------------------
+def reference_goldens():
+    """outputs of the UNMODIFIED reference on the named configs (tests/golden/golden_configs.npz, made by
+    tests/golden/make_golden_configs.py in the build container), or {} if the file is absent"""
+    try:
+        return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_configs.npz")))
+    except Exception:
+        return {}
+
+
 def c3_adata():
     import recipes
     spl, vel, genes = recipes.coupling_panel(C3_GENES, C3_CELLS, 3)
@@ -436,6 +445,14 @@ def ours_arm(args):
             "gpu_launches": int(launches_all),
             "roofline": roof,
         }
+        gold = reference_goldens()
+        if "c3_matrix" in gold:
+            M3 = np.zeros((C3_GENES, C3_GENES))
+            M3[plan["src"], plan["dst"]] = np.where(np.isnan(vals), 0.0, vals)
+            sub = M3[np.ix_(recipes.C3_TFS, recipes.C3_TARGETS)]
+            line["parity_vs_reference"] = {"max_abs_diff": float(np.abs(sub - gold["c3_matrix"]).max()), "pairs": int(sub.size),
+                                           "source": "unmodified reference's causal_net_dynamics_coupling on 5 TFs x 8 targets of this "
+                                                     "workload (tests/golden/golden_configs.npz: c3_matrix)"}
         if invariance is not None:
             line["invariance_ok"] = invariance
         if extras:
@@ -542,6 +559,23 @@ def extra_c2(args, h, S, timed, steps, peaks, peak_src, cores):
            "e2e": {"value": n_jobs / e2e_s, "unit": "evals/s", "api": "causal_model(DataFrame).rdi([1,5,10]), one call"},
            "roofline": roofline_of(acc, steps, "ksg_sweepw_kernel<1,6,2,false>", h.sm_count, peaks, peak_src, step_ms=ms,
                                    traffic=ncu_traffic("c2:ksg_sweepw_kernel<1,6,2,false>"))}
+    gold = reference_goldens()
+    if "c2full_rdi_1" in gold:
+        per = plan["per"]
+        diff, gmax, rmax = 0.0, np.full((G, G), -np.inf), np.full((G, G), -np.inf)
+        for i, d in enumerate(C2_DELAYS):
+            Md = np.full((G, G), np.nan); Md[plan["src"], plan["tgt"]] = vals[i * per:(i + 1) * per]
+            ref = gold["c2full_rdi_%d" % d]
+            diff = max(diff, float(np.nanmax(np.abs(Md - ref))))
+            gmax = np.fmax(gmax, Md); rmax = np.fmax(rmax, ref)
+
+        def top(M, n=100):
+            a, b = np.nonzero(~np.eye(G, dtype=bool))
+            o_ = np.lexsort((b, a, -M[a, b]))[:n]
+            return list(zip(a[o_].tolist(), b[o_].tolist()))
+
+        rec["parity_vs_reference"] = {"max_abs_diff": diff, "values": 3 * G * (G - 1), "top100_ranking_identical": top(gmax) == top(rmax),
+                                      "source": "the FULL matrix of this workload from the unmodified reference (golden_configs.npz: c2full_rdi_*)"}
     if not args.no_cpu:
         rng = np.random.default_rng(0)
         sample = []
@@ -590,6 +624,30 @@ def extra_c5(args, h, S, D, timed, peaks, peak_src, cores, rank, world):
            "full_config_extrapolated_s": 2997000 / (len(jobs) / (ms * 1e-3)),
            "roofline": roofline_of(acc, 2, "ksg_sweepw_kernel<1,6,2,true> + kde_sweep_kernel<2,2>", h.sm_count, peaks, peak_src, weighted=True,
                                    step_ms=ms, traffic=ncu_traffic("c5:ksg_sweepw_kernel<1,6,2,true>"))}
+    if world >= 8 and not args.no_full_c5:
+        # north_star's target run: ALL ordered pairs x 3 delays of the 1000-gene panel (2 997 000 cumi evaluations) through the
+        # public API, one call, on this box's GPUs; parity on the pairs the unmodified reference was run on
+        import pandas as pd
+        import torch
+        import torch.distributed as dist
+        frame = pd.DataFrame(E, index=pd.Index(["g%04d" % i for i in range(G)], name="GENE_ID"))
+        model = S.causal_model(frame)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = model.rdi(C2_DELAYS, uniformization=True)
+        dist.barrier(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        n_full = G * (G - 1) * 3
+        full = {"jobs": n_full, "wall_s": wall, "value": n_full / wall, "unit": "evals/s", "n_gpus": world,
+                "api": "causal_model(DataFrame 1000 x 20000).rdi([1,5,10], uniformization=True), one call, matrix upload included"}
+        gold = reference_goldens()
+        if "c5_urdi_1" in gold:
+            gi = recipes.C5_GENES
+            full["parity_vs_reference"] = {
+                "max_abs_diff": max(float(np.nanmax(np.abs(res[d].to_numpy(dtype=float)[np.ix_(gi, gi)] - gold["c5_urdi_%d" % d])))
+                                    for d in C2_DELAYS),
+                "values": 36, "source": "unmodified reference's rdi(uniformization=True) on 4 genes of this panel (golden_configs.npz: c5_urdi_*)"}
+        rec["full_config"] = full
     if not args.no_cpu and world == 1:
         # the reference's cumi at N = 20 000 takes ~10 s alone and far longer when every core runs one (memory-bound kd-tree
         # KDE): a handful of jobs keeps this leg bounded
@@ -625,6 +683,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (C2, C5 slab)")
+    ap.add_argument("--no-full-c5", action="store_true", help="at 8 GPUs: skip the full C5 sweep (2,997,000 evaluations, ~15 s)")
     args = ap.parse_args()
     global OUT
     OUT = _json_only_stdout()
