@@ -41,6 +41,9 @@ namespace scribe {
 #ifndef SWEEPW_UNROLL_CW
 #define SWEEPW_UNROLL_CW SWEEPW_UNROLL_W
 #endif
+#ifndef SWEEPW_DIAG
+#define SWEEPW_DIAG 0                     // 1: diagnostics build (visited_kde reports the count-pass visits inside the lane's own window)
+#endif
 #ifndef SWEEPW_WFMA
 #define SWEEPW_WFMA 0                     // 1: weighted count pass accumulates W_yz with an indicator DFMA instead of a predicated DADD
 #endif
@@ -627,9 +630,15 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
     double wyz[Q], wz[Q];
     #pragma unroll
     for (int q = 0; q < Q; q++) wyz[q] = wz[q] = 0.0;
+#if SWEEPW_DIAG
+    unsigned long long useful = 0;
+#endif
 
     // per-chunk epilogue shared by both forms of the scan: masks -> counts
     auto tally = [&](int q, int base, unsigned zw, unsigned mx, unsigned my, unsigned mz) {
+#if SWEEPW_DIAG
+        useful += __popc(zw);                                      // candidates of this chunk inside the lane's own key window
+#endif
         if (DZ == 0) {
             nxz[q] += __popc(zw & mx);                             // n_xy: x-ball inside the y-window
         } else if (!WEIGHTED) {
@@ -897,6 +906,13 @@ ksg_sweepw_kernel(const JobDesc* __restrict__ jobs, int warps_per_job, int k, co
         partial[(size_t)job * warps_per_job + wj] = acc;
         if (visited) { atomicAdd(visited, nvis * 32ull * 32ull); atomicAdd(visited + 1, nvis2 * 32ull * 32ull); }
     }
+#if SWEEPW_DIAG
+    {   // diagnostics build only: how many of the count-pass visits fall inside the visiting lane's own window (visited[2], unweighted)
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) useful += __shfl_down_sync(0xffffffffu, useful, o);
+        if (lane == 0 && visited && !WEIGHTED) atomicAdd(visited + 2, useful);
+    }
+#endif
 }
 
 }  // namespace scribe
