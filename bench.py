@@ -340,9 +340,14 @@ def ours_arm(args):
         vals = SC._coupling_execute(plan)
         return vals, h.stats()
 
+    # the e2e step's inputs live in PINNED host memory (bench contract): the layers are copied once, outside the timed region,
+    # into page-locked buffers that the library's cudaMemcpyAsync then reads at PCIe speed
+    spl_pin = torch.from_numpy(spl).pin_memory().numpy()
+    vel_pin = torch.from_numpy(vel).pin_memory().numpy()
+
     def step_e2e():
         l2_flush()
-        a = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
+        a = recipes.FakeAnnData({"spliced": spl_pin, "velocity": vel_pin}, genes)
         S.causal_net_dynamics_coupling(a)
         return a.uns["causal_net"]["RDI"], h.stats()
 
@@ -441,7 +446,7 @@ def ours_arm(args):
             "e2e": {"value": n_jobs * e2e_steps / (e2e_ms * 1e-3), "unit": "evals/s", "h2d_bytes_per_step": int(h2d / e2e_steps),
                     "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "scribe_py_b200.causal_net_dynamics_coupling(adata) -> adata.uns['causal_net']['RDI'] (raw layers uploaded "
-                           "and normalised on the device every step)"},
+                           "from pinned host memory and normalised on the device every step)"},
             "gpu_launches": int(launches_all),
             "roofline": roof,
         }
