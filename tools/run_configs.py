@@ -16,15 +16,7 @@ from scribe_py_b200 import _lib
 from oracle import ref_port, ksg_oracle
 
 
-def ar_panel(G, T, seed):
-    """cheap autocorrelated expression panel with sparse lagged couplings (vectorised over genes)"""
-    rng = np.random.default_rng(seed)
-    E = np.zeros((G, T + 60)); E[:, :12] = rng.standard_normal((G, 12))
-    par = rng.integers(0, G, (G, 2)); dl = rng.choice([1, 5, 10], (G, 2)); co = rng.uniform(0.4, 0.9, (G, 2)) * rng.choice([-1, 1], (G, 2))
-    noise = 0.3 * rng.standard_normal((G, T + 60))
-    for t in range(12, T + 60):
-        E[:, t] = 0.9 * E[:, t - 1] + noise[:, t] + co[:, 0] * np.tanh(E[par[:, 0], t - dl[:, 0]]) + co[:, 1] * np.tanh(E[par[:, 1], t - dl[:, 1]])
-    return E[:, 60:]
+ar_panel = recipes.ar_panel          # the C4 / C5 generator lives with the other seeded recipes (tests/golden/recipes.py)
 
 
 def cpu_check(fn, argsets):
@@ -117,19 +109,15 @@ def run_rdi(name, G, T, delays, uniform, seed, n_check, L=None):
 
 
 def run_c3(G, N, n_check):
+    spl, vel, genes = recipes.coupling_panel(G, N, 3)
     rng = np.random.default_rng(3)
-    spl = rng.gamma(2., 1., (N, G)); spl[rng.random((N, G)) < 0.2] = 0
-    par = rng.integers(0, G, (G, 2)); co = rng.uniform(-0.5, 0.5, (G, 2))
-    vel = co[:, 0] * (spl[:, par[:, 0]] - spl[:, par[:, 0]].mean(0)) + co[:, 1] * (spl[:, par[:, 1]] - spl[:, par[:, 1]].mean(0)) \
-        - 0.2 * spl + 0.1 * rng.standard_normal((N, G))
-    genes = ["g%04d" % i for i in range(G)]
     ad = recipes.FakeAnnData({"spliced": spl, "velocity": vel}, genes)
     h = _lib.default_handle()
     S.causal_net_dynamics_coupling(recipes.FakeAnnData({"spliced": spl[:, :8], "velocity": vel[:, :8]}, genes[:8]))   # warm-up
     walls = []
     for _ in range(3):              # the first full-size call also pays for the growth of the device workspaces
         barrier(); t = time.perf_counter(); S.causal_net_dynamics_coupling(ad); barrier(); walls.append(time.perf_counter() - t)
-    wall = min(walls)
+    wall = float(np.median(walls))          # a drop-in user calls once: the first call (workspace growth included) is reported beside it
     st = h.stats()
     M = ad.uns["causal_net"]["RDI"].to_numpy(dtype=float)
     s = (spl - spl.mean(0)) / (spl.max(0) - spl.min(0)); v = (vel - vel.mean(0)) / (vel.max(0) - vel.min(0))
@@ -143,7 +131,7 @@ def run_c3(G, N, n_check):
     return report("C3 dynamics coupling %d genes x %d cells" % (G, N), G * (G - 1), wall, st,
                   {"parity_max_abs_diff": float(np.abs(ref - np.array(got)).max()) if WORLD == 1 else None, "parity_jobs": n_check,
                    "estimator_ms_last_chunk": st["estimator_ms"], "mean_cells_kept": float(np.mean([len(a[0]) for a in args])),
-                   "wall_s_each_call": walls})
+                   "first_call_s": walls[0], "wall_s_each_call": walls})
 
 
 def init_distributed():
